@@ -1,0 +1,112 @@
+/*
+ * sph3d_b200.h -- C ABI of libsph3d_b200.so: the SPH3D-GCN per-layer hot path on B200 (sm_100a).
+ *
+ * One entry point per host launcher of the reference (14 launchers in
+ * /root/reference/tf_ops/<op>/tf_<op>_gpu.cu); each prototype cites the launcher it replaces and
+ * keeps that launcher's argument ORDER, followed by (workspace,) stream.  Differences that are
+ * deliberate:
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing is allocated or freed here;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), never synchronises
+ *     the host, never touches the legacy default stream, and is CUDA-graph capturable;
+ *   - outputs are written completely by the call (the zero fill the TensorFlow glue did with
+ *     cudaMemset before each launch -- tf_<op>.cpp -- is folded into the kernels), so the caller
+ *     may pass uninitialised buffers;
+ *   - the return value is a cudaError_t as int (0 = cudaSuccess; 1 = cudaErrorInvalidValue for a
+ *     bad dimension/attribute, the analogue of the glue's errors::InvalidArgument).
+ *
+ * Layouts are the reference's: contiguous row-major, int32 indices, fp32 features.
+ *   database (B,N,3)  query (B,M,3)  nn_index (B,M,K)  nn_count (B,M)  nn_dist (B,M,K)
+ *   input (B,N,C)  filter (F,C,r)  output (B,M,C*r) with cout = c*r + j
+ */
+#ifndef SPH3D_B200_H_
+#define SPH3D_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH3D_B200_ABI_VERSION 1
+int sph3d_abi_version(void);
+
+/* Last launch geometry chosen by the library for `what` (diagnostics for bench.py / DESIGN.md):
+ * returns the number of kernels the most recent call of that entry point enqueued. */
+int sph3d_last_launch_count(void);
+
+/* ---- a1: buildSphereNeighborLauncher, tf_nnquery_gpu.cu:115-121 (kernel :15-65) --------------
+ * Ball query with the reference's growing-radius chain semantics: bit-exact
+ * nn_index / nn_count / nn_dist.  radius > 0, K > 0. */
+int sph3d_build_sphere_neighbor(int B, int N, int M, int K, float radius,
+                                const float* database, const float* query,
+                                int* nn_index, int* nn_count, float* nn_dist, void* stream);
+
+/* ---- a2: buildCubeNeighborLauncher, tf_nnquery_gpu.cu:123-127 (kernel :72-113) ---------------
+ * nn_index is (B,M,K,2): (point id, grid bin) interleaved; nn_count may be 0. */
+int sph3d_build_cube_neighbor(int B, int N, int M, int grid_size, int K, float length,
+                              const float* database, const float* query,
+                              int* nn_index, int* nn_count, void* stream);
+
+/* ---- a3: sphericalKernelLauncher, tf_buildkernel_gpu.cu:83-89 (kernel :20-79) ----------------
+ * n>2 even, p>0 even, q>0, radius>0 (tf_buildkernel.cpp:39-49). filt_index in [0, n*p*q]. */
+int sph3d_spherical_kernel(int B, int N, int M, int K, int n, int p, int q, float radius,
+                           const float* database, const float* query, const int* nn_index,
+                           const int* nn_count, const float* nn_dist, int* filt_index, void* stream);
+
+/* ---- a4: depthwiseConv3dLauncher, tf_conv3d_gpu.cu:107-113 (kernel :7-29) --------------------
+ * F (number of filter bins) is needed to stage the filter; the reference read it only in the
+ * gradient launcher. */
+int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, int K,
+                           const int* nn_index, const int* nn_count, const int* bin_index,
+                           const float* input, const float* filter, float* output, void* stream);
+
+/* ---- a5: depthwiseConv3dGradLauncher, tf_conv3d_gpu.cu:115-140 (kernels :32-101) -------------
+ * workspace: sph3d_depthwise_conv3d_grad_workspace_bytes(...) bytes of device scratch (per-CTA
+ * filter-gradient partials, reduced in a fixed order => grad_filter is deterministic). */
+size_t sph3d_depthwise_conv3d_grad_workspace_bytes(int B, int N, int M, int F, int C, int r, int K);
+int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, int r, int K,
+                                const int* nn_index, const int* nn_count, const int* bin_index,
+                                const float* input, const float* filter, const float* grad_output,
+                                float* grad_input, float* grad_filter,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6: farthestPointSampleLauncher, tf_sample_gpu.cu:77-80 (kernel :7-73) ------------------
+ * temp: the reference's (32,n) scratch (tf_sample.cpp:50) becomes a caller-owned workspace of
+ * sph3d_farthest_point_sample_workspace_bytes(b,n,m) bytes (0 when the cloud fits on chip). */
+size_t sph3d_farthest_point_sample_workspace_bytes(int b, int n, int m);
+int sph3d_farthest_point_sample(int b, int n, int m, const float* inp, void* temp, size_t temp_bytes,
+                                int* out, void* stream);
+
+/* ---- a8: maxPool3dLauncher / maxPool3dGradLauncher, tf_pool3d_gpu.cu:93-105 ------------------ */
+int sph3d_max_pool3d(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
+                     const float* input, float* output, int* max_index, void* stream);
+int sph3d_max_pool3d_grad(int B, int N, int M, int C, const int* max_index,
+                          const float* grad_output, float* grad_input, void* stream);
+
+/* ---- a9: avgPool3dLauncher / avgPool3dGradLauncher, tf_pool3d_gpu.cu:107-119 ----------------- */
+int sph3d_avg_pool3d(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
+                     const float* input, float* output, void* stream);
+int sph3d_avg_pool3d_grad(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
+                          const float* grad_output, float* grad_input, void* stream);
+
+/* ---- a10: meanInterpolateLauncher / GradLauncher, tf_unpool3d_gpu.cu:87-99 -------------------
+ * As in the reference, N = fine (output) points, M = coarse (input) points:
+ * input (B,M,C), nn_index (B,N,K) into the coarse cloud, output (B,N,C). */
+int sph3d_mean_interpolate(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
+                           const float* input, float* output, void* stream);
+int sph3d_mean_interpolate_grad(int B, int N, int M, int C, int K, const int* nn_index,
+                                const int* nn_count, const float* grad_output, float* grad_input,
+                                void* stream);
+
+/* ---- a11: weightedInterpolateLauncher / GradLauncher, tf_unpool3d_gpu.cu:101-113 ------------- */
+int sph3d_weighted_interpolate(int B, int N, int M, int C, int K, const int* nn_index,
+                               const int* nn_count, const float* input, const float* weight,
+                               float* output, void* stream);
+int sph3d_weighted_interpolate_grad(int B, int N, int M, int C, int K, const int* nn_index,
+                                    const int* nn_count, const float* grad_output, const float* weight,
+                                    float* grad_input, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH3D_B200_H_ */

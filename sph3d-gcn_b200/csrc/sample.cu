@@ -1,0 +1,250 @@
+// sample.cu -- farthest point sampling, sm_100a.
+//
+// Replaces farthestPointSampleLauncher (/root/reference/tf_ops/sampling/tf_sample_gpu.cu:77-80,
+// kernel :7-73).  FPS is `npoint` strictly sequential rounds, so the only thing that matters is
+// the latency of one round.  The reference keeps the running min-distance array in GLOBAL memory
+// (re-read and re-written every round), reads the picked point's coordinates from global memory
+// and reduces with a 10-level shared-memory tree (11 __syncthreads per round), one CTA per cloud.
+//
+// Here a cloud lives entirely in REGISTERS of one thread-block cluster: CS CTAs x 1024 threads,
+// each thread owns P points (xyz + running min distance = 4P registers, loaded once).  A round is
+//   P x (3 FADD, FMUL, 2 FFMA, FMNMX, compare/select)                      -- no memory traffic
+//   two REDUX.SYNC per warp (max of the float bits, then min of the tie key)
+//   one 20-byte record per warp written straight into EVERY cluster CTA's shared memory (DSMEM)
+//   ONE barrier (bar.sync for CS=1, barrier.cluster for CS>1), double-buffered records
+//   every warp re-reduces the 32*CS records itself (no second barrier, no broadcast step); the
+//   record carries the winner's coordinates, so the next round starts without a global load.
+//
+// Exact selection rule of the reference: argmax of the running min distance, ties to
+// the smallest (k mod 1024), then to the smallest k.  Thread `tid` of every CTA owns only points
+// with k mod 1024 == tid, in ascending k, with a strict '>' scan -- the reference thread's own rule --
+// and the cross-thread rule is carried by the key (tid << 21 | k >> 10), minimised among maxima.
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "../../include/sph3d_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace sph3d {
+
+constexpr int FPS_THREADS = 1024;
+
+template <int CS>
+struct FpsSlots {
+    int bits[2][CS * 32];
+    int key[2][CS * 32];
+    float x[2][CS * 32], y[2][CS * 32], z[2][CS * 32];
+};
+
+// reduce (bits,key) records: max bits, then min key.  Returns winner key; bits via reference.
+__device__ __forceinline__ void warp_argmax(int bits, int key, int& wbits, int& wkey)
+{
+    wbits = __reduce_max_sync(FULL_MASK, bits);
+    wkey = __reduce_min_sync(FULL_MASK, bits == wbits ? key : 0x7fffffff);
+}
+
+template <int CS, int P>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* __restrict__ out)
+{
+    __shared__ FpsSlots<CS> slots;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int rank = 0;
+    if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
+    const int cloud = blockIdx.x / CS;
+    const float* pts = xyz + (size_t)cloud * N * 3;
+
+    float px[P], py[P], pz[P], td[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        int k = (p * CS + rank) * FPS_THREADS + tid;
+        if (k < N) { px[p] = __ldg(pts + 3 * k); py[p] = __ldg(pts + 3 * k + 1); pz[p] = __ldg(pts + 3 * k + 2); td[p] = 1e38f; }
+        else { px[p] = py[p] = pz[p] = 0.f; td[p] = -1.f; }       // never beats best = -1
+    }
+    float x1 = __ldg(pts), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
+    if (rank == 0 && tid == 0) out[(size_t)cloud * npoint] = 0;
+
+    for (int j = 1; j < npoint; j++) {
+        const int buf = j & 1;
+        float best = -1.f; int bp = 0;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            float d = sqdist_ref(__fsub_rn(px[p], x1), __fsub_rn(py[p], y1), __fsub_rn(pz[p], z1));
+            float d2 = fminf(d, td[p]);
+            td[p] = d2;
+            if (d2 > best) { best = d2; bp = p; }
+        }
+        const int bits = __float_as_int(best);
+        const int key = (tid << 21) | (bp * CS + rank);
+        int wbits, wkey;
+        warp_argmax(bits, key, wbits, wkey);
+        // winner lane publishes its coordinates to the warp
+        float wx = px[0], wy = py[0], wz = pz[0];
+#pragma unroll
+        for (int p = 1; p < P; p++) if (bp == p) { wx = px[p]; wy = py[p]; wz = pz[p]; }
+        const int src = __ffs(__ballot_sync(FULL_MASK, bits == wbits && key == wkey)) - 1;
+        wx = __shfl_sync(FULL_MASK, wx, src);
+        wy = __shfl_sync(FULL_MASK, wy, src);
+        wz = __shfl_sync(FULL_MASK, wz, src);
+        const int e = rank * 32 + warp;
+        if constexpr (CS == 1) {
+            if (lane == 0) {
+                slots.bits[buf][e] = wbits; slots.key[buf][e] = wkey;
+                slots.x[buf][e] = wx; slots.y[buf][e] = wy; slots.z[buf][e] = wz;
+            }
+            __syncthreads();
+        } else {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (lane < CS) {
+                FpsSlots<CS>* rs = cluster.map_shared_rank(&slots, lane);
+                rs->bits[buf][e] = wbits; rs->key[buf][e] = wkey;
+                rs->x[buf][e] = wx; rs->y[buf][e] = wy; rs->z[buf][e] = wz;
+            }
+            cluster.sync();
+        }
+        // every warp reduces the 32*CS records
+        int mb = slots.bits[buf][lane], mk = slots.key[buf][lane], me = lane;
+#pragma unroll
+        for (int c = 1; c < CS; c++) {
+            int ob = slots.bits[buf][c * 32 + lane], ok = slots.key[buf][c * 32 + lane];
+            if (ob > mb || (ob == mb && ok < mk)) { mb = ob; mk = ok; me = c * 32 + lane; }
+        }
+        int gb, gk;
+        warp_argmax(mb, mk, gb, gk);
+        const int wl = __ffs(__ballot_sync(FULL_MASK, mb == gb && mk == gk)) - 1;
+        const int we = __shfl_sync(FULL_MASK, me, wl);
+        x1 = slots.x[buf][we]; y1 = slots.y[buf][we]; z1 = slots.z[buf][we];
+        if (rank == 0 && tid == 0) out[(size_t)cloud * npoint + j] = ((gk & 0x1fffff) << 10) | (gk >> 21);
+    }
+    if constexpr (CS > 1) cg::this_cluster().sync();       // no CTA may exit while peers still write its smem
+}
+
+// Any-N fallback: one CTA per cloud, running min distances in a global workspace.
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_global_kernel(int B, int N, int npoint, const float* __restrict__ xyz, float* __restrict__ temp,
+                  int* __restrict__ out)
+{
+    __shared__ FpsSlots<1> slots;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int cloud = blockIdx.x; cloud < B; cloud += gridDim.x) {
+        const float* pts = xyz + (size_t)cloud * N * 3;
+        float* td = temp + (size_t)cloud * N;
+        for (int k = tid; k < N; k += FPS_THREADS) td[k] = 1e38f;
+        float x1 = __ldg(pts), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
+        if (tid == 0) out[(size_t)cloud * npoint] = 0;
+        __syncthreads();
+        for (int j = 1; j < npoint; j++) {
+            const int buf = j & 1;
+            float best = -1.f; int bk = 0; float bx = 0.f, by = 0.f, bz = 0.f;
+            for (int k = tid; k < N; k += FPS_THREADS) {
+                float x2 = __ldg(pts + 3 * k), y2 = __ldg(pts + 3 * k + 1), z2 = __ldg(pts + 3 * k + 2);
+                float d = sqdist_ref(__fsub_rn(x2, x1), __fsub_rn(y2, y1), __fsub_rn(z2, z1));
+                float d2 = fminf(d, td[k]);
+                td[k] = d2;
+                if (d2 > best) { best = d2; bk = k; bx = x2; by = y2; bz = z2; }
+            }
+            const int bits = __float_as_int(best);
+            const int key = (tid << 21) | (bk >> 10);
+            int wbits, wkey;
+            warp_argmax(bits, key, wbits, wkey);
+            const int src = __ffs(__ballot_sync(FULL_MASK, bits == wbits && key == wkey)) - 1;
+            float wx = __shfl_sync(FULL_MASK, bx, src), wy = __shfl_sync(FULL_MASK, by, src), wz = __shfl_sync(FULL_MASK, bz, src);
+            if (lane == 0) {
+                slots.bits[buf][warp] = wbits; slots.key[buf][warp] = wkey;
+                slots.x[buf][warp] = wx; slots.y[buf][warp] = wy; slots.z[buf][warp] = wz;
+            }
+            __syncthreads();
+            int gb, gk;
+            const int mb = slots.bits[buf][lane], mk = slots.key[buf][lane];
+            warp_argmax(mb, mk, gb, gk);
+            const int wl = __ffs(__ballot_sync(FULL_MASK, mb == gb && mk == gk)) - 1;
+            x1 = slots.x[buf][wl]; y1 = slots.y[buf][wl]; z1 = slots.z[buf][wl];
+            if (tid == 0) out[(size_t)cloud * npoint + j] = ((gk & 0x1fffff) << 10) | (gk >> 21);
+        }
+        __syncthreads();
+    }
+}
+
+struct FpsPlan { int cs, p; };
+
+static FpsPlan plan_fps(int n)
+{
+    const int cs_opts[4] = {1, 2, 4, 8};
+    for (int i = 0; i < 4; i++) {
+        int cs = cs_opts[i];
+        int p = (n + cs * FPS_THREADS - 1) / (cs * FPS_THREADS);
+        if (p <= 8) return FpsPlan{cs, p};
+    }
+    int p = (n + 8 * FPS_THREADS - 1) / (8 * FPS_THREADS);
+    if (p <= 10) return FpsPlan{8, p};
+    return FpsPlan{0, 0};
+}
+
+template <int CS, int P>
+static cudaError_t launch_fps(int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * CS);
+    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CS, P>, B, N, npoint, xyz, out);
+}
+
+template <int CS>
+static cudaError_t launch_fps_p(int p, int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
+{
+    switch (p) {
+        case 1: return launch_fps<CS, 1>(B, N, npoint, xyz, out, st);
+        case 2: return launch_fps<CS, 2>(B, N, npoint, xyz, out, st);
+        case 3: return launch_fps<CS, 3>(B, N, npoint, xyz, out, st);
+        case 4: return launch_fps<CS, 4>(B, N, npoint, xyz, out, st);
+        case 5: return launch_fps<CS, 5>(B, N, npoint, xyz, out, st);
+        case 6: return launch_fps<CS, 6>(B, N, npoint, xyz, out, st);
+        case 7: return launch_fps<CS, 7>(B, N, npoint, xyz, out, st);
+        case 8: return launch_fps<CS, 8>(B, N, npoint, xyz, out, st);
+        default: break;
+    }
+    if (CS == 8 && p == 9) return launch_fps<8, 9>(B, N, npoint, xyz, out, st);
+    if (CS == 8 && p == 10) return launch_fps<8, 10>(B, N, npoint, xyz, out, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sph3d
+
+using namespace sph3d;
+
+extern "C" size_t sph3d_farthest_point_sample_workspace_bytes(int b, int n, int m)
+{
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    FpsPlan p = plan_fps(n);
+    return p.cs ? 0 : sizeof(float) * (size_t)b * n;
+}
+
+extern "C" int sph3d_farthest_point_sample(int b, int n, int m, const float* inp, void* temp, size_t temp_bytes,
+                                           int* out, void* stream)
+{
+    g_last_launch_count = 0;
+    if (b <= 0 || n <= 0 || m <= 0 || !inp || !out) return (int)cudaErrorInvalidValue;   // tf_sample.cpp:34 npoint>0
+    if (n > (1 << 30)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    FpsPlan p = plan_fps(n);
+    cudaError_t e;
+    if (p.cs == 0) {
+        if (!temp || temp_bytes < sizeof(float) * (size_t)b * n) return (int)cudaErrorInvalidValue;
+        int grid = b < sm_count() ? b : sm_count();
+        fps_global_kernel<<<grid, FPS_THREADS, 0, st>>>(b, n, m, inp, (float*)temp, out);
+        e = cudaPeekAtLastError();
+    } else if (p.cs == 1) e = launch_fps_p<1>(p.p, b, n, m, inp, out, st);
+    else if (p.cs == 2) e = launch_fps_p<2>(p.p, b, n, m, inp, out, st);
+    else if (p.cs == 4) e = launch_fps_p<4>(p.p, b, n, m, inp, out, st);
+    else e = launch_fps_p<8>(p.p, b, n, m, inp, out, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    g_last_launch_count = 1;
+    return 0;
+}

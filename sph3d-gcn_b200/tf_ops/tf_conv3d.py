@@ -1,0 +1,82 @@
+"""Depthwise spherical convolution -- mirrors /root/reference/tf_ops/convolution/tf_conv3d.py:10-32
+(op + its registered gradient).  Index inputs receive no gradient, as there."""
+import torch
+
+from .. import _lib
+
+
+def _check(input, filter, nn_index, nn_count, bin_index):
+    input = _lib.cuda_tensor(input, torch.float32, 3, "input")
+    filter = _lib.cuda_tensor(filter, torch.float32, 3, "filter")
+    nn_index = _lib.cuda_tensor(nn_index, torch.int32, 3, "nn_index")
+    nn_count = _lib.cuda_tensor(nn_count, torch.int32, 2, "nn_count")
+    bin_index = _lib.cuda_tensor(bin_index, torch.int32, 3, "bin_index")
+    if filter.shape[1] != input.shape[2]:
+        raise ValueError("Input Channel size error of the filter")        # tf_conv3d.cpp:67
+    if bin_index.shape != nn_index.shape or nn_count.shape != nn_index.shape[:2] or nn_index.shape[0] != input.shape[0]:
+        raise ValueError("nn_index / nn_count / bin_index shapes are inconsistent")
+    return input, filter, nn_index, nn_count, bin_index
+
+
+def _forward(input, filter, nn_index, nn_count, bin_index):
+    B, N, C = input.shape
+    F, _, r = filter.shape
+    M, K = nn_index.shape[1], nn_index.shape[2]
+    output = torch.empty((B, M, C * r), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        rc = _lib.lib().sph3d_depthwise_conv3d(B, N, M, F, C, r, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
+                                               _lib.ptr(bin_index), _lib.ptr(input), _lib.ptr(filter),
+                                               _lib.ptr(output), _lib.stream_ptr())
+    _lib.check(rc, "depthwise_conv3d")
+    return output
+
+
+def depthwise_conv3d_grad(input, filter, grad_output, nn_index, nn_count, bin_index):
+    """conv3d_module.depthwise_conv3d_grad of the reference (tf_conv3d.py:30): -> (grad_input, grad_filter)."""
+    input, filter, nn_index, nn_count, bin_index = _check(input, filter, nn_index, nn_count, bin_index)
+    grad_output = _lib.cuda_tensor(grad_output, torch.float32, 3, "grad_output")
+    B, N, C = input.shape
+    F, _, r = filter.shape
+    M, K = nn_index.shape[1], nn_index.shape[2]
+    if grad_output.shape != (B, M, C * r):
+        raise ValueError("grad_output must be (batch, mpoint, in_channels*multiplier)")
+    L = _lib.lib()
+    grad_input = torch.empty((B, N, C), dtype=torch.float32, device=input.device)
+    grad_filter = torch.empty((F, C, r), dtype=torch.float32, device=input.device)
+    ws_bytes = L.sph3d_depthwise_conv3d_grad_workspace_bytes(B, N, M, F, C, r, K)
+    ws = torch.empty((max(ws_bytes // 4, 1),), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        rc = L.sph3d_depthwise_conv3d_grad(B, N, M, F, C, r, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
+                                           _lib.ptr(bin_index), _lib.ptr(input), _lib.ptr(filter),
+                                           _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.ptr(grad_filter),
+                                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    _lib.check(rc, "depthwise_conv3d_grad")
+    return grad_input, grad_filter
+
+
+class _DepthwiseConv3d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, filter, nn_index, nn_count, bin_index):
+        ctx.save_for_backward(input, filter, nn_index, nn_count, bin_index)
+        return _forward(input, filter, nn_index, nn_count, bin_index)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, filter, nn_index, nn_count, bin_index = ctx.saved_tensors
+        gi, gf = depthwise_conv3d_grad(input, filter, grad_output.contiguous(), nn_index, nn_count, bin_index)
+        return gi, gf, None, None, None
+
+
+def depthwise_conv3d(input, filter, nn_index, nn_count, bin_index):
+    '''
+    Input:
+        input:   (batch, npoint, in_channels) float32 array, input point features
+        filter: (binsize, in_channels, channel_multiplier) float32 array, convolution filter
+        nn_index: (batch, mpoint, nnsample) int32 array, neighbor indices
+        nn_count: (batch, mpoint) int32 array, number of neighbors
+        bin_index: (batch, mpoint, nnsample), filtet bins' indices
+    Output:
+        output: (batch, mpoint, out_channels) float32 array, output point features
+    '''
+    input, filter, nn_index, nn_count, bin_index = _check(input, filter, nn_index, nn_count, bin_index)
+    return _DepthwiseConv3d.apply(input, filter, nn_index, nn_count, bin_index)

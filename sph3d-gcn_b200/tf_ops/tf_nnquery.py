@@ -1,0 +1,80 @@
+"""Neighbour queries -- mirrors /root/reference/tf_ops/nnquery/tf_nnquery.py:9-60.
+No gradient (ops.NoGradient there; plain non-differentiable index outputs here)."""
+import torch
+
+from .. import _lib
+
+
+def _xyz(t, name):
+    t = _lib.cuda_tensor(t, torch.float32, 3, name)
+    if t.shape[2] < 3:
+        raise ValueError("Shape of %s points requires to be (batch, npoint, 3)" % name)
+    return t[:, :, 0:3].contiguous()       # reference slices [:, :, 0:3] (tf_nnquery.py:26-27)
+
+
+@torch.no_grad()
+def build_sphere_neighbor(database, query, radius=0.1, dilation_rate=None, nnsample=100):
+    '''
+    Input:
+        database: (batch, npoint, 3+x) float32 array, database points
+        query:    (batch, mpoint, 3) float32 array, query points
+        radius:   float32, range search radius
+        dilation_rate: float32, dilation rate of range search
+        nnsample: int32, maximum number of neighbors to be sampled
+    Output:
+        nn_index: (batch, mpoint, nnsample) int32 array, neighbor indices
+        nn_count: (batch, mpoint) int32 array, number of neighbors
+        nn_dist:  (batch, mpoint, nnsample) float32, sqrt distance array
+    '''
+    database = _xyz(database, "database")
+    query = _xyz(query, "query")
+    if dilation_rate is not None:
+        radius = dilation_rate * radius
+    if not radius > 0:
+        raise ValueError("Range search requires radius>0, got %r" % (radius,))
+    if not nnsample > 0:
+        raise ValueError("BuildSphereNeighbor requires nn_sample>0, got %r" % (nnsample,))
+    B, N, _ = database.shape
+    if query.shape[0] != B:
+        raise ValueError("database and query must have the same batch size")
+    M, K = query.shape[1], int(nnsample)
+    dev = database.device
+    nn_index = torch.empty((B, M, K), dtype=torch.int32, device=dev)
+    nn_count = torch.empty((B, M), dtype=torch.int32, device=dev)
+    nn_dist = torch.empty((B, M, K), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sph3d_build_sphere_neighbor(B, N, M, K, float(radius), _lib.ptr(database), _lib.ptr(query),
+                                                    _lib.ptr(nn_index), _lib.ptr(nn_count), _lib.ptr(nn_dist),
+                                                    _lib.stream_ptr())
+    _lib.check(rc, "build_sphere_neighbor")
+    return nn_index, nn_count, nn_dist
+
+
+@torch.no_grad()
+def build_cube_neighbor(database, query, length=0.1, dilation_rate=None, nnsample=100, gridsize=3):
+    '''
+    Output:
+        nn_index: (batch, mpoint, nnsample, 2) int32 array, neighbor and filter bin indices
+        nn_count: (batch, mpoint) int32 array, number of neighbors
+    '''
+    database = _xyz(database, "database")
+    query = _xyz(query, "query")
+    if dilation_rate is not None:
+        length = dilation_rate * length
+    if not length > 0:
+        raise ValueError("Cube size requires length>0, got %r" % (length,))
+    if not nnsample > 0:
+        raise ValueError("BuildSphereNeighbor requires nn_sample>0, got %r" % (nnsample,))
+    if not gridsize > 0:
+        raise ValueError("Need grid_size_>0, got %r" % (gridsize,))
+    B, N, _ = database.shape
+    M, K = query.shape[1], int(nnsample)
+    dev = database.device
+    nn_index = torch.empty((B, M, K, 2), dtype=torch.int32, device=dev)
+    nn_count = torch.empty((B, M), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sph3d_build_cube_neighbor(B, N, M, int(gridsize), K, float(length), _lib.ptr(database),
+                                                  _lib.ptr(query), _lib.ptr(nn_index), _lib.ptr(nn_count),
+                                                  _lib.stream_ptr())
+    _lib.check(rc, "build_cube_neighbor")
+    return nn_index, nn_count

@@ -1,0 +1,335 @@
+"""Layer library with the signatures of the reference's utils/sph3gcn_util.py, on PyTorch.
+
+Every public function keeps the reference's name, positional order, defaults and return arity
+(/root/reference/utils/sph3gcn_util.py:20-332) so the call sites in models/SPH3D_*.py carry over
+unchanged; tensors are torch CUDA tensors and the six custom ops are the sm_100a kernels behind
+include/sph3d_b200.h.  TensorFlow-isms are re-hosted as follows:
+
+  tf.variable_scope(scope, reuse) + tf.get_variable  -> a module-level VariableStore keyed by
+      "scope/name"; a variable is created on first use and re-used afterwards (eager execution
+      calls the layer function every step, so `reuse` is accepted and ignored);
+  tf.add_to_collection('losses', ...)                 -> get_collection('losses') (cleared by the caller
+      once per step with clear_collections());
+  tf.contrib.layers.xavier_initializer()              -> Glorot uniform with TF's fan computation;
+  tf.layers.batch_normalization(momentum=0.99)        -> batch norm over the last axis, eps 1e-3,
+      biased batch variance, moving statistics updated with 0.99 decay, L2 terms of beta/gamma in
+      get_collection('regularization_losses');
+  is_training                                         -> Python bool (or 0-dim tensor).
+
+Order of operations in the conv layers is the reference's: matmul -> bias -> activation -> BN.
+"""
+import contextlib
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+if __package__ in (None, ""):           # flat import from sys.path, the way the reference scripts do it
+    import importlib
+    import os
+    import sys
+    _root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if _root not in sys.path:
+        sys.path.insert(0, _root)
+    _pkg = importlib.import_module("sph3d_gcn_b200")
+    sys.modules[__name__] = _pkg.utils.sph3gcn_util
+else:
+    from ..tf_ops import tf_conv3d, tf_pool3d, tf_unpool3d
+    from ..tf_ops.tf_nnquery import build_sphere_neighbor, build_cube_neighbor
+    from ..tf_ops.tf_sample import farthest_point_sample, inverse_density_sample, random_sample
+    from ..tf_ops.tf_buildkernel import spherical_kernel
+
+    neighbor_fn = build_sphere_neighbor  # default nn search method
+
+    elu = F.elu
+
+
+    # ------------------------------------------------------------------ variable store / scopes
+    class VariableStore(object):
+        def __init__(self):
+            self.params = OrderedDict()       # name -> torch.nn.Parameter
+            self.buffers = OrderedDict()      # name -> tensor (BN moving statistics)
+            self.collections = {"losses": [], "regularization_losses": []}
+            self.scope = []
+
+        def full_name(self, name):
+            return "/".join(self.scope + [name])
+
+
+    _STORE = VariableStore()
+
+
+    def get_variable_store():
+        return _STORE
+
+
+    def reset_variables():
+        """Drop every variable (a fresh tf.Graph)."""
+        global _STORE
+        _STORE = VariableStore()
+        return _STORE
+
+
+    def trainable_variables():
+        return list(_STORE.params.values())
+
+
+    def named_variables():
+        return OrderedDict(_STORE.params)
+
+
+    def get_collection(name):
+        return list(_STORE.collections.get(name, []))
+
+
+    def clear_collections():
+        for v in _STORE.collections.values():
+            del v[:]
+
+
+    @contextlib.contextmanager
+    def variable_scope(scope, reuse=None):
+        _STORE.scope.append(str(scope))
+        try:
+            yield scope
+        finally:
+            _STORE.scope.pop()
+
+
+    def _fans(shape):
+        # tf.contrib.layers.xavier_initializer / variance_scaling fan computation
+        if len(shape) < 1:
+            return 1.0, 1.0
+        if len(shape) == 1:
+            return float(shape[0]), float(shape[0])
+        receptive = 1.0
+        for d in shape[:-2]:
+            receptive *= d
+        return float(shape[-2]) * receptive, float(shape[-1]) * receptive
+
+
+    def get_variable(name, shape, initializer, device, trainable=True):
+        full = _STORE.full_name(name)
+        table = _STORE.params if trainable else _STORE.buffers
+        if full in table:
+            return table[full]
+        t = torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, device=device)
+        initializer(t)
+        if trainable:
+            t = torch.nn.Parameter(t)
+        table[full] = t
+        return t
+
+
+    def _variable_with_weight_decay(name, shape, stddev, with_decay, use_xavier=True, device=None):
+        """Initialized variable with optional L2 weight decay (sph3gcn_util.py:61-85)."""
+        if use_xavier:
+            fan_in, fan_out = _fans(shape)
+            limit = (6.0 / (fan_in + fan_out)) ** 0.5
+
+            def initializer(t):
+                with torch.no_grad():
+                    t.uniform_(-limit, limit)
+        else:
+            def initializer(t):
+                torch.nn.init.trunc_normal_(t, mean=0.0, std=stddev, a=-2 * stddev, b=2 * stddev)
+        var = get_variable(name, shape, initializer, device)
+        if with_decay is not None:
+            _STORE.collections["losses"].append(0.5 * var.pow(2).sum() * with_decay)   # tf.nn.l2_loss * decay
+        return var
+
+
+    def _zeros_variable(name, shape, device):
+        return get_variable(name, shape, lambda t: t.zero_(), device)
+
+
+    # ------------------------------------------------------------------ graph builders
+    def build_global_graph(xyz, query, radius):
+        nn_uplimit = xyz.shape[1]
+        nn_idx, nn_cnt, nn_dst = neighbor_fn(xyz, query, radius=radius, nnsample=nn_uplimit)
+        return nn_idx, nn_cnt, nn_dst
+
+
+    def build_graph(xyz, radius, nn_uplimit, num_sample, sample_method=None):
+        intra_idx, intra_cnt, intra_dst = neighbor_fn(xyz, xyz, radius=radius, nnsample=nn_uplimit)
+
+        if num_sample is not None:
+            if sample_method == 'random':
+                sample_index = random_sample(num_sample, xyz)
+            elif sample_method == 'FPS':
+                sample_index = farthest_point_sample(num_sample, xyz)
+            elif sample_method == 'IDS':
+                prob = intra_dst.sum(dim=-1) / intra_cnt.to(torch.float32)
+                sample_index = inverse_density_sample(num_sample, prob)
+            else:
+                raise ValueError('Unknown sampling method.')
+
+            batch_size = xyz.shape[0]
+            batch_indices = torch.arange(batch_size, device=xyz.device, dtype=sample_index.dtype)
+            batch_indices = batch_indices.view(-1, 1, 1).expand(-1, int(num_sample), 1)
+            indices = torch.cat([batch_indices, sample_index.unsqueeze(2)], dim=2)   # (B,S,2) = [batch, point]
+        else:
+            indices = None
+
+        return intra_idx, intra_cnt, intra_dst, indices
+
+
+    def build_graph_deconv(xyz, xyz_unpool, radius, nn_uplimit):
+        intra_idx, intra_cnt, intra_dst = neighbor_fn(xyz, xyz, radius=radius, nnsample=nn_uplimit)
+        inter_idx, inter_cnt, inter_dst = neighbor_fn(xyz, xyz_unpool, radius=radius, nnsample=nn_uplimit)
+        return intra_idx, intra_cnt, intra_dst, inter_idx, inter_cnt, inter_dst
+
+
+    def gather_nd(params, indices):
+        """tf.gather_nd(params, indices) for the (B,S,2) = [batch, point] indices build_graph returns:
+        the row selection the models apply to xyz / intra_idx / intra_cnt / intra_dst
+        (models/SPH3D_s3dis.py:68-72)."""
+        b = indices[..., 0].long()
+        s = indices[..., 1].long()
+        return params[b, s].contiguous()
+
+
+    # ------------------------------------------------------------------ layers
+    def _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training):
+        if with_bias:
+            biases = _zeros_variable('biases', [num_out_channels], outputs.device)
+            outputs = outputs + biases
+        if activation_fn is not None:
+            outputs = activation_fn(outputs)
+        if with_bn:
+            outputs = batch_normalization(outputs, is_training, name='bn', reuse=reuse)
+        return outputs
+
+
+    def separable_conv3d(inputs,
+                         num_out_channels,
+                         kernel_size,
+                         depth_multiplier,
+                         scope,
+                         nn_index,
+                         nn_count,
+                         filt_index,
+                         use_xavier=True,
+                         stddev=1e-3,
+                         weight_decay=None,
+                         activation_fn=elu,
+                         with_bn=False,
+                         with_bias=False,
+                         reuse=None,
+                         is_training=None):
+        """ 3D separable convolution with non-linear operation (sph3gcn_util.py:88-163).
+            inputs BxNxC -> depthwise spherical conv (BxMxC*r) -> pointwise matmul -> B x M x num_out_channels
+        """
+        with variable_scope(scope, reuse=reuse):
+            num_in_channels = inputs.shape[-1]
+            depthwise_kernel_shape = [kernel_size, num_in_channels, depth_multiplier]
+            depthwise_kernel = _variable_with_weight_decay('depthwise_weights', shape=depthwise_kernel_shape,
+                                                           use_xavier=use_xavier, stddev=stddev,
+                                                           with_decay=weight_decay, device=inputs.device)
+            outputs = tf_conv3d.depthwise_conv3d(inputs, depthwise_kernel, nn_index, nn_count, filt_index)
+
+            batch_size = outputs.shape[0]
+            num_in_channels = outputs.shape[-1]
+            kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
+                                                 use_xavier=use_xavier, stddev=stddev,
+                                                 with_decay=weight_decay, device=inputs.device)
+            outputs = torch.matmul(outputs.reshape(-1, num_in_channels), kernel)
+            outputs = outputs.reshape(batch_size, -1, num_out_channels)
+            return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
+
+
+    def pointwise_conv3d(inputs,
+                         num_out_channels,
+                         scope,
+                         use_xavier=True,
+                         stddev=1e-3,
+                         weight_decay=None,
+                         activation_fn=elu,
+                         with_bn=False,
+                         with_bias=False,
+                         reuse=None,
+                         is_training=None):
+        """ pointwise convolution with non-linear operation (sph3gcn_util.py:166-222). """
+        with variable_scope(scope, reuse=reuse):
+            batch_size = inputs.shape[0]
+            num_in_channels = inputs.shape[-1]
+            kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
+                                                 use_xavier=use_xavier, stddev=stddev,
+                                                 with_decay=weight_decay, device=inputs.device)
+            outputs = torch.matmul(inputs.reshape(-1, num_in_channels), kernel)
+            outputs = outputs.reshape(batch_size, -1, num_out_channels)
+            return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
+
+
+    def fully_connected(inputs,
+                        num_out_channels,
+                        scope,
+                        use_xavier=True,
+                        stddev=1e-3,
+                        weight_decay=None,
+                        activation_fn=elu,
+                        with_bn=False,
+                        with_bias=False,
+                        reuse=None,
+                        is_training=None):
+        """ Fully connected layer with non-linear operation (sph3gcn_util.py:225-273). inputs BxC. """
+        with variable_scope(scope, reuse=reuse):
+            num_in_channels = inputs.shape[-1]
+            kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
+                                                 use_xavier=use_xavier, stddev=stddev,
+                                                 with_decay=weight_decay, device=inputs.device)
+            outputs = torch.matmul(inputs, kernel)
+            return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
+
+
+    def pool3d(inputs, nn_index, nn_count, scope, method):
+        """ 3D pooling (sph3gcn_util.py:276-297). """
+        with variable_scope(scope):
+            if method == 'max':
+                outputs, max_index = tf_pool3d.max_pool3d(inputs, nn_index, nn_count)
+            elif method == 'avg':
+                outputs = tf_pool3d.avg_pool3d(inputs, nn_index, nn_count)
+            else:
+                raise ValueError("Unknow pooling method %s." % method)
+            return outputs
+
+
+    def unpool3d(inputs, nn_index, nn_count, nn_dist, scope, method):
+        """ 3D unpooling (sph3gcn_util.py:300-325). """
+        with variable_scope(scope):
+            if method == 'mean':
+                outputs = tf_unpool3d.mean_interpolate(inputs, nn_index, nn_count)
+            elif method == 'weighted':
+                sum_nn_dist = nn_dist.sum(dim=-1, keepdim=True)
+                epsilon = 1e-7
+                weight = (nn_dist + epsilon) / (sum_nn_dist + epsilon)
+                outputs = tf_unpool3d.weighted_interpolate(inputs, weight, nn_index, nn_count)
+            else:
+                raise ValueError("Unknow unpooling method %s." % method)
+            return outputs
+
+
+    def batch_normalization(data, is_training, name, reuse=None):
+        """tf.layers.batch_normalization(data, momentum=0.99, training=is_training, ...) over the last
+        axis, with L2 regularizers (scale 1.0) on beta and gamma (sph3gcn_util.py:328-332)."""
+        momentum, eps = 0.99, 1e-3
+        C = data.shape[-1]
+        with variable_scope(name, reuse=reuse):
+            gamma = get_variable('gamma', [C], lambda t: t.fill_(1.0), data.device)
+            beta = get_variable('beta', [C], lambda t: t.zero_(), data.device)
+            moving_mean = get_variable('moving_mean', [C], lambda t: t.zero_(), data.device, trainable=False)
+            moving_var = get_variable('moving_variance', [C], lambda t: t.fill_(1.0), data.device, trainable=False)
+        _STORE.collections["regularization_losses"].append(0.5 * beta.pow(2).sum())
+        _STORE.collections["regularization_losses"].append(0.5 * gamma.pow(2).sum())
+        training = bool(is_training) if is_training is not None else False
+        flat = data.reshape(-1, C)
+        if training:
+            mean = flat.mean(dim=0)
+            var = flat.var(dim=0, unbiased=False)
+            with torch.no_grad():
+                moving_mean.mul_(momentum).add_(mean.detach(), alpha=1 - momentum)
+                moving_var.mul_(momentum).add_(var.detach(), alpha=1 - momentum)
+        else:
+            mean, var = moving_mean, moving_var
+        out = (flat - mean) * torch.rsqrt(var + eps) * gamma + beta
+        return out.reshape(data.shape)
