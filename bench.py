@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SPH3D-GCN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfgT|cfg1|s3dis_l1]
+
+A "step" is one pass of the depthwise spherical convolution, forward + backward (grad_input and
+grad_filter), over one batch of synthetic point clouds -- BASELINE.json's metric
+("points/sec SPH3D conv fwd+bwd") on its headline shape Cfg-T: B=32 clouds x N=M=10000 points,
+K=64 neighbours, Cin=128, multiplier 1, 8x2x2+1 = 33 spherical bins.  Neighbour and bin indices
+come from this library's own (oracle-verified) ball query + spherical kernel on seeded uniform
+clouds with the saturating radius of BASELINE.md, so the graph has real spatial structure.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job points/s with inputs resident in HBM;
+`e2e` = the same metric through the public op (tf_conv3d.depthwise_conv3d -> ctypes -> C ABI) with
+every input coming from pinned HOST memory and every result read back, copies inside the timed region;
+`roofline` = algorithmic bytes / CUDA-event time of the dominant kernel vs MEASURED_PEAKS.json;
+`cpu_baseline` = the CPU oracle port (oracle/sph3d_oracle.c, OpenMP) on a bounded sample, rank 0, N=1;
+`ref_gpu` (extra) = the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same inputs, same GPU.
+
+--impl reference: the reference's implementation of this path.  The reference has NO CPU kernels
+(every REGISTER_KERNEL_BUILDER is DEVICE_GPU), so its "own implementation" is its CUDA kernels:
+this arm runs oracle/_ref (unmodified tf_ops/*_gpu.cu, their <<<32,1024>>> launches, the glue's
+cudaMemset zero fills) on the GPU; if oracle/_ref did not travel it falls back to the CPU oracle port.
+Under torchrun only rank 0 works.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: B, N, K, C, r, kernel
+    "cfgT": dict(B=32, N=10000, K=64, C=128, r=1, kernel=(8, 2, 2)),
+    "cfgT_r2": dict(B=32, N=10000, K=64, C=128, r=2, kernel=(8, 2, 2)),
+    "s3dis_l1": dict(B=8, N=8192, K=64, C=64, r=2, kernel=(8, 2, 2)),
+    "cfg1": dict(B=2, N=1024, K=20, C=3, r=2, kernel=(8, 2, 2)),
+}
+METRIC = "points/sec SPH3D conv fwd+bwd"
+
+
+def saturating_radius(N, K):
+    return float((3.0 * 2 * K / (4.0 * np.pi * N)) ** (1.0 / 3.0))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons during the timed region (pynvml; nvidia-smi equivalent)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:          # no NVML: report that rather than inventing numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": sorted(self.reasons)}
+
+
+def make_inputs(cfg, seed, dev, S):
+    """seeded synthetic clouds -> graph (this library's nnquery + buildkernel) -> conv operands, on `dev`."""
+    B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
+    n, p, q = cfg["kernel"]
+    F = n * p * q + 1
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xyz = torch.rand(B, N, 3, generator=g, dtype=torch.float32)           # uniform cube; i.i.d. => already unordered
+    x = torch.randn(B, N, C, generator=g, dtype=torch.float32)
+    W = 0.1 * torch.randn(F, C, r, generator=g, dtype=torch.float32)
+    go = torch.randn(B, N, C * r, generator=g, dtype=torch.float32)
+    radius = saturating_radius(N, K)
+    xyz_d = xyz.to(dev)
+    idx, cnt, dst = S.tf_nnquery.build_sphere_neighbor(xyz_d, xyz_d, radius=radius, nnsample=K)
+    filt = S.tf_buildkernel.spherical_kernel(xyz_d, xyz_d, idx, cnt, dst, radius, kernel=[n, p, q])
+    host = dict(x=x, W=W, go=go, idx=idx.cpu(), cnt=cnt.cpu(), filt=filt.cpu(), xyz=xyz)
+    return host, radius, F
+
+
+def algorithmic_bytes(B, N, M, C, r, F, E):
+    fwd = 4 * (B * N * C + B * M * C * r + 2 * E + B * M + F * C * r)
+    bwd = 4 * (B * M * C * r + 2 * B * N * C + 2 * E + B * M + 2 * F * C * r)
+    return fwd, bwd
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed ncu summary (profiles/ncu_summary.json), if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        return json.load(open(p))["kernels"][kernel_key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def cpu_baseline(host, cfg, target_seconds=12.0):
+    """CPU oracle port (conv forward in the reference's fp32 order + fp64 backward) on a bounded sample."""
+    import oracle as O
+    O.build()
+    B = cfg["B"]
+    a = lambda t, n: t[:n].numpy()
+
+    def run(nb):
+        t0 = time.perf_counter()
+        O.depthwise_conv3d(a(host["x"], nb), host["W"].numpy(), a(host["idx"], nb), a(host["cnt"], nb), a(host["filt"], nb), mode=0)
+        O.depthwise_conv3d_grad(a(host["x"], nb), host["W"].numpy(), a(host["go"], nb), a(host["idx"], nb), a(host["cnt"], nb), a(host["filt"], nb))
+        return time.perf_counter() - t0
+    t1 = run(1)
+    nb = int(max(1, min(B, target_seconds / max(t1, 1e-3))))
+    t = run(nb) if nb > 1 else t1
+    return {"value": nb * cfg["N"] / t, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d of %d clouds of the same workload, conv fwd (fp32 reference order) + bwd (fp64), OpenMP, %.2f s" % (nb, B, t)}
+
+
+def ref_gpu_times(dev_in, cfg, F, iters=2):
+    """unmodified reference kernels (oracle/_ref) on the same device-resident inputs: ms per fwd / bwd."""
+    import ref_gpu as R
+    if not R.available():
+        return None
+    B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
+    M = N
+    x, W, go, idx, cnt, filt = (dev_in[k] for k in ("x", "W", "go", "idx", "cnt", "filt"))
+    out = torch.empty(B, M, C * r, device=x.device)
+    gi, gf = torch.empty(B, N, C, device=x.device), torch.empty(F, C, r, device=x.device)
+    torch.cuda.synchronize()
+    res = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # the reference launchers use the legacy default stream; torch's current stream is also the legacy
+    # default stream unless changed, so CUDA events recorded through torch bracket them correctly.
+    for name, fn in (("fwd", lambda: (out.zero_(), R.launch_raw("conv", B, N, M, C, r, K, idx, cnt, filt, x, W, out))),
+                     ("bwd", lambda: (gi.zero_(), gf.zero_(), R.launch_raw("conv_grad", B, N, M, F, C, r, K, idx, cnt, filt, x, W, go, gi, gf)))):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        res[name + "_ms"] = e0.elapsed_time(e1) / iters
+    res["points_per_s"] = B * M / ((res["fwd_ms"] + res["bwd_ms"]) * 1e-3)
+    res["what"] = "unmodified reference kernels (tf_conv3d_gpu.cu, <<<32,1024>>>) incl. the glue's zero fills"
+    return res
+
+
+def run_reference_arm(args):
+    """--impl reference (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
+    line = {"impl": "reference", "metric": METRIC, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": args.workload, **{k: cfg[k] for k in ("B", "N", "K", "C", "r")}}}
+    import sph3d_gcn_b200 as S
+    import ref_gpu as R
+    use_gpu = torch.cuda.is_available() and R.available() and not args.reference_cpu
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        host, radius, F = make_inputs(cfg, 1234 + 2, dev, S)
+    else:
+        line["unavailable"] = "no CUDA device: inputs for this workload are built with the GPU ball query"
+        print(json.dumps(line)); return
+    M = N
+    if use_gpu:
+        pin = {k: v.pin_memory() for k, v in host.items() if k != "xyz"}
+        d = {k: v.to(dev) for k, v in pin.items()}
+        out = torch.empty(B, M, C * r, device=dev); gi = torch.empty(B, N, C, device=dev); gf = torch.empty(F, C, r, device=dev)
+        h_out, h_gi, h_gf = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out, gi, gf))
+
+        def step():
+            out.zero_(); R.launch_raw("conv", B, N, M, C, r, K, d["idx"], d["cnt"], d["filt"], d["x"], d["W"], out)
+            gi.zero_(); gf.zero_()
+            R.launch_raw("conv_grad", B, N, M, F, C, r, K, d["idx"], d["cnt"], d["filt"], d["x"], d["W"], d["go"], gi, gf)
+
+        def step_e2e():
+            for k in ("x", "W", "go", "idx", "cnt", "filt"):
+                d[k].copy_(pin[k], non_blocking=True)
+            step()
+            h_out.copy_(out, non_blocking=True); h_gi.copy_(gi, non_blocking=True); h_gf.copy_(gf, non_blocking=True)
+        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))       # bounded: these kernels are slow
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        step_e2e(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step_e2e()
+        e1.record(); torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / steps
+        h2d = sum(pin[k].numel() * pin[k].element_size() for k in ("x", "W", "go", "idx", "cnt", "filt"))
+        d2h = sum(t.numel() * t.element_size() for t in (out, gi, gf))
+        line.update(value=B * M / (ms * 1e-3), ms_per_step=ms, steps=steps, warmup=warm, gpu_launches=0,
+                    e2e={"value": B * M / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    cpu_baseline={"value": B * M / (ms * 1e-3), "unit": "points/s", "cores": 0, "kind": "reference",
+                                  "sample": "UNMODIFIED reference CUDA kernels (oracle/_ref) on the GPU: the reference has no CPU "
+                                            "implementation of this path; full workload, %d steps" % steps})
+    else:
+        cb = cpu_baseline(host, cfg, target_seconds=20.0)
+        line.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb, gpu_launches=0,
+                    e2e={"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfgT", choices=sorted(WORKLOADS))
+    ap.add_argument("--reference-cpu", action="store_true", help="--impl reference: force the CPU oracle port")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / ref_gpu legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    import sph3d_gcn_b200 as S
+    from importlib import import_module
+    dist_util = import_module("sph3d_gcn_b200.utils.dist_util")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    cfg = WORKLOADS[args.workload]
+    B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
+    M = N
+    host, radius, F = make_inputs(cfg, 1234 + 2 + rank, dev, S)       # weak scaling: every rank owns B clouds
+    pin = {k: v.pin_memory() for k, v in host.items() if k != "xyz"}
+    d = {k: v.to(dev) for k, v in pin.items()}
+    E = int(d["cnt"].sum().item())
+    L = S._lib.lib()
+
+    x = d["x"].clone().requires_grad_(True)
+    Wp = d["W"].clone().requires_grad_(True)
+
+    def step(timers=None):
+        """one hot-path pass through the public op: forward, backward, DP all-reduce of the weight gradient"""
+        x.grad = None; Wp.grad = None
+        if timers: timers[0].record()
+        out = S.tf_conv3d.depthwise_conv3d(x, Wp, d["idx"], d["cnt"], d["filt"])
+        if timers: timers[1].record()
+        out.backward(d["go"])
+        if timers: timers[2].record()
+        dist_util.allreduce_gradients([Wp.grad])
+        return out
+
+    def step_e2e(h):
+        for k in ("x", "W", "go", "idx", "cnt", "filt"):
+            d[k].copy_(pin[k], non_blocking=True)
+        with torch.no_grad():
+            x.copy_(d["x"]); Wp.copy_(d["W"])
+        out = step()
+        h[0].copy_(out.detach(), non_blocking=True); h[1].copy_(x.grad, non_blocking=True); h[2].copy_(Wp.grad, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = 0
+    S.tf_conv3d._forward(d["x"], d["W"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
+    S.tf_conv3d.depthwise_conv3d_grad(d["x"], d["W"], d["go"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        step(ev[i])
+    t1.record()
+    barrier()
+    clocks = sampler.result()
+    ms_total = t0.elapsed_time(t1)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = world * B * M / (ms_step * 1e-3)
+
+    # ---- end-to-end: host buffers in, results out, every step -------------------------------------
+    h = [torch.empty(B, M, C * r).pin_memory(), torch.empty(B, N, C).pin_memory(), torch.empty(F, C, r).pin_memory()]
+    e2e_steps = args.steps
+    for _ in range(3):
+        step_e2e(h)
+    barrier()
+    t0.record()
+    for _ in range(e2e_steps):
+        step_e2e(h)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt.item())
+    ms_e2e /= e2e_steps
+    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ("x", "W", "go", "idx", "cnt", "filt"))
+    d2h = sum(t.numel() * t.element_size() for t in h)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab_fwd, ab_bwd = algorithmic_bytes(B, N, M, C, r, F, E)
+        dominant = "conv_bwd_kernel" if bwd_ms >= fwd_ms else "conv_fwd_kernel"
+        ab, tms = (ab_bwd, bwd_ms) if dominant == "conv_bwd_kernel" else (ab_fwd, fwd_ms)
+        ach = ab / (tms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "B_per_gpu": B, "N": N, "M": M, "K": K, "Cin": C, "multiplier": r,
+                       "bins": F, "radius": radius, "mean_neighbors": E / (B * M), "parallelism": "dp%d" % world,
+                       "l2": "inputs (%.0f MB/step) larger than L2, no flush" % ((ab_fwd + ab_bwd) / 2e6)},
+            "clocks": clocks,
+            "e2e": {"value": world * B * M / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic(dominant), "peak_source": peak_src, "algorithmic_bytes": ab,
+                         "kernel_ms": tms},
+            "kernels": {"conv_fwd_ms": fwd_ms, "conv_bwd_ms": bwd_ms,
+                        "conv_fwd_gbs": ab_fwd / (fwd_ms * 1e-3) / 1e9, "conv_bwd_gbs": ab_bwd / (bwd_ms * 1e-3) / 1e9,
+                        "conv_fwd_frac": ab_fwd / (fwd_ms * 1e-3) / 1e9 / peak, "conv_bwd_frac": ab_bwd / (bwd_ms * 1e-3) / 1e9 / peak,
+                        "logical_gather_gbs_fwd": (4.0 * E * C + 4.0 * B * M * C * r + 8.0 * E) / (fwd_ms * 1e-3) / 1e9},
+        }
+        if world == 1 and not args.no_extras:
+            try:
+                line["cpu_baseline"] = cpu_baseline(host, cfg)
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+            try:
+                line["ref_gpu"] = ref_gpu_times(d, cfg, F)
+            except Exception as e:
+                line["ref_gpu"] = {"error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,8 +30,7 @@ extern "C" {
 #define SPH3D_B200_ABI_VERSION 1
 int sph3d_abi_version(void);
 
-/* Last launch geometry chosen by the library for `what` (diagnostics for bench.py / DESIGN.md):
- * returns the number of kernels the most recent call of that entry point enqueued. */
+/* Number of KERNELS (memsets excluded) the most recent entry-point call enqueued (bench.py gpu_launches). */
 int sph3d_last_launch_count(void);
 
 /* ---- a1: buildSphereNeighborLauncher, tf_nnquery_gpu.cu:115-121 (kernel :15-65) --------------

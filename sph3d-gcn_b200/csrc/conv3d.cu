@@ -426,7 +426,7 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
                                                                               bin_index, input, filter, grad_output,
                                                                               grad_input, grad_filter);
         SPH3D_CHECK_LAUNCH();
-        g_last_launch_count = 3;
+        g_last_launch_count = 1;
         return 0;
     }
     size_t need = (size_t)p.grid_x * F * C * r * sizeof(float);
@@ -453,7 +453,7 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
     size_t n = (size_t)F * C * r;
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.grid_x, n, part, grad_filter);
     SPH3D_CHECK_LAUNCH();
-    g_last_launch_count = 3;
+    g_last_launch_count = 2;        // kernels only (the cudaMemsetAsync of grad_input is not counted)
     return 0;
 }
 

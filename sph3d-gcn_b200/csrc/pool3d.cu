@@ -196,7 +196,7 @@ static int launch_scatter(int B, int S, int Rr, int C, int K, const int* nn_inde
     else if (vec == 2) row_scatter_kernel<2, OP><<<grid, POOL_WARPS * 32, 0, st>>>(B, S, Rr, C, K, nn_index, nn_count, weight, grad_output, grad_input);
     else row_scatter_kernel<1, OP><<<grid, POOL_WARPS * 32, 0, st>>>(B, S, Rr, C, K, nn_index, nn_count, weight, grad_output, grad_input);
     SPH3D_CHECK_LAUNCH();
-    g_last_launch_count = 2;
+    g_last_launch_count = 1;
     return 0;
 }
 
@@ -225,7 +225,7 @@ extern "C" int sph3d_max_pool3d_grad(int B, int N, int M, int C, const int* max_
     size_t total = (size_t)B * M * C, want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
     max_pool_grad_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(B, N, M, C, max_index, grad_output, grad_input);
     SPH3D_CHECK_LAUNCH();
-    g_last_launch_count = 2;
+    g_last_launch_count = 1;
     return 0;
 }
 
