@@ -1,0 +1,291 @@
+// conv_bwd.cu -- depthwise spherical graph convolution, backward (grad_input + grad_filter), sm_100a.
+//
+// Replaces depthwiseConv3dGradLauncher (/root/reference/tf_ops/convolution/tf_conv3d_gpu.cu:115-140,
+// kernels depthwise_input_backward :32-55 and depthwise_filter_backward :58-101) and the cudaMemset
+// zero fills of tf_conv3d.cpp:152-153.
+//
+//   grad_input [b, nn[b,m,k], c]  += sum_j gO[b,m,c*r+j] * W[bin[b,m,k], c, j] / cnt
+//   grad_filter[bin[b,m,k], c, j] +=       gO[b,m,c*r+j] * in[b, nn[b,m,k], c] / cnt
+//
+// ONE fused pass.  A group of 8 warps shares one output row; warp w of the group OWNS the filter
+// bins f = w, w+8, w+16, ... (SLOTS of them).  For each of its bins that occurs in the row (ballot) it
+//   - forms d = sum_j g*W[f] once (filter strip from shared memory),
+//   - walks the bin's edges: gathers the input strip (LDG.128), adds it to a running sum (FADD2) and
+//     scatters d into grad_input with ONE 16-byte vector reduction per lane (REDG.ADD.F32x4),
+//   - folds g * sum(in) into its REGISTER accumulator for that bin.
+// Because bins are owned, the filter gradient needs no atomics and no shared-memory accumulation at
+// all: every warp keeps SLOTS x (VEC*R) accumulators in registers for the whole kernel and writes
+// them once, as a per-CTA partial that a second tiny kernel sums in a fixed order (deterministic
+// grad_filter).  The reference instead issues E*C*r shared-memory float atomics per 48 KB filter
+// window and re-runs the whole pass ceil(F*C*r/12288) times (Q13/Q14).
+#include "conv_common.cuh"
+#include "../../include/sph3d_b200.h"
+
+namespace sph3d {
+
+constexpr int BWD_GROUP = 8;     // warps sharing one row; warp-in-group = owner of bins w, w+8, ...
+
+template <int VEC, int R, int SLOTS>
+__global__ void __launch_bounds__((R == 1 && SLOTS <= 5) ? 1024 : 512, 1)
+conv_bwd_kernel(int B, int N, int M, int F, int C, int K,
+                const int* __restrict__ nn_index, const int* __restrict__ nn_count,
+                const int* __restrict__ bin_index, const float* __restrict__ input,
+                const float* __restrict__ filter, const float* __restrict__ grad_output,
+                float* __restrict__ grad_input, float* __restrict__ gw_partial)
+{
+    constexpr int E = VEC * R;
+    using S = SmemStrip<E>;
+    extern __shared__ __align__(16) float smem[];
+    float* Wsh = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wig = warp % BWD_GROUP, group = warp / BWD_GROUP, ngroups = (blockDim.x >> 5) / BWD_GROUP;
+    const int cbase = blockIdx.y * 32 * VEC;
+    stage_filter<VEC, R>(Wsh, filter, F, C, cbase);
+    __syncthreads();
+
+    const int c0 = cbase + lane * VEC;
+    const bool active = c0 < C;
+    float acc[SLOTS][E];
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++)
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[s][e] = 0.f;
+
+    const long long rows = (long long)B * M;
+    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long rbeg = chunk * ROWS_PER_CHUNK;
+        const long long rend = rbeg + ROWS_PER_CHUNK < rows ? rbeg + ROWS_PER_CHUNK : rows;
+        for (long long row = rbeg + group; row < rend; row += ngroups) {
+            const int b = (int)(row / M);
+            const int cnt = min(__ldg(nn_count + row), K);
+            if (cnt <= 0) continue;
+            const float* inb = input + (size_t)b * N * C + c0;
+            float* gib = grad_input + (size_t)b * N * C + c0;
+            const int* idxrow = nn_index + (size_t)row * K;
+            const int* binrow = bin_index + (size_t)row * K;
+            float g[E];
+            {
+                const float inv = 1.0f / (float)cnt;
+                const float* go = grad_output + (size_t)row * C * R + (size_t)c0 * R;
+                constexpr int VW = strip_vw(E);
+#pragma unroll
+                for (int pl = 0; pl < E / VW; pl++) {
+                    float t[VW];
+                    VecIO<VW>::ld(t, go + pl * VW, active);
+#pragma unroll
+                    for (int u = 0; u < VW; u++) g[pl * VW + u] = t[u] * inv;
+                }
+            }
+            for (int kt = 0; kt < cnt; kt += 64) {
+                const int k0 = kt + lane, k1 = kt + 32 + lane;
+                int i0 = 0, b0 = -1, i1 = 0, b1 = -1;
+                if (k0 < cnt) { i0 = __ldg(idxrow + k0); b0 = __ldg(binrow + k0); }
+                if (k1 < cnt) { i1 = __ldg(idxrow + k1); b1 = __ldg(binrow + k1); }
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    const int f = wig + s * BWD_GROUP;
+                    if (f < F) {
+                        unsigned m0 = __ballot_sync(FULL_MASK, b0 == f);
+                        unsigned m1 = __ballot_sync(FULL_MASK, b1 == f);
+                        if (m0 | m1) {
+                            float w[E];
+                            S::load(w, Wsh + f * S::FLOATS, lane);
+                            float d[VEC], sv[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; v++) {
+                                float t = 0.f;
+#pragma unroll
+                                for (int j = 0; j < R; j++) t = fmaf(g[v * R + j], w[v * R + j], t);
+                                d[v] = t; sv[v] = 0.f;
+                            }
+                            auto edges = [&](unsigned m, int myidx) {
+                                while (m) {
+                                    const int n0 = __shfl_sync(FULL_MASK, myidx, pop_highest(m));
+                                    float v0[VEC];
+                                    VecIO<VEC>::ld(v0, inb + (size_t)n0 * C, active);
+                                    if (active) VecIO<VEC>::red(gib + (size_t)n0 * C, d);
+                                    if (m) {
+                                        const int n1 = __shfl_sync(FULL_MASK, myidx, pop_highest(m));
+                                        float v1[VEC];
+                                        VecIO<VEC>::ld(v1, inb + (size_t)n1 * C, active);
+                                        if (active) VecIO<VEC>::red(gib + (size_t)n1 * C, d);
+                                        strip_add<VEC>(sv, v1);
+                                    }
+                                    strip_add<VEC>(sv, v0);
+                                }
+                            };
+                            edges(m0, i0);
+                            edges(m1, i1);
+#pragma unroll
+                            for (int e = 0; e < E; e++) acc[s][e] = fmaf(g[e], sv[e / R], acc[s][e]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // per-CTA partial [blockIdx.x][group][f][c][j]: each (f, c-chunk) is written by exactly one warp
+    float* part = gw_partial + ((size_t)blockIdx.x * ngroups + group) * F * C * R;
+    if (active) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) {
+            const int f = wig + s * BWD_GROUP;
+            if (f < F) {
+                float* dst = part + ((size_t)f * C + c0) * R;
+                constexpr int VW = strip_vw(E);
+#pragma unroll
+                for (int pl = 0; pl < E / VW; pl++) {
+                    float t[VW];
+#pragma unroll
+                    for (int u = 0; u < VW; u++) t[u] = acc[s][pl * VW + u];
+                    VecIO<VW>::st(dst + pl * VW, t);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(int P, size_t n, const float* __restrict__ part, float* __restrict__ out)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p = 0;
+        for (; p + 3 < P; p += 4) {
+            s0 += part[(size_t)p * n + t]; s1 += part[(size_t)(p + 1) * n + t];
+            s2 += part[(size_t)(p + 2) * n + t]; s3 += part[(size_t)(p + 3) * n + t];
+        }
+        for (; p < P; p++) s0 += part[(size_t)p * n + t];
+        out[t] = (s0 + s1) + (s2 + s3);
+    }
+}
+
+// generic fallback (any r, any F): float atomics, like the reference but parallel over the whole grid
+__global__ void __launch_bounds__(256)
+conv_bwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict__ nn_index,
+                 const int* __restrict__ nn_count, const int* __restrict__ bin_index,
+                 const float* __restrict__ input, const float* __restrict__ filter,
+                 const float* __restrict__ grad_output, float* __restrict__ grad_input,
+                 float* __restrict__ grad_filter)
+{
+    const int Co = C * r;
+    const size_t total = (size_t)B * M * Co;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        size_t row = t / Co;
+        int co = (int)(t - row * Co), ci = co / r, b = (int)(row / M);
+        int cnt = min(__ldg(nn_count + row), K);
+        if (cnt <= 0) continue;
+        float g = __ldg(grad_output + t) / (float)cnt;
+        for (int k = 0; k < cnt; k++) {
+            int n = __ldg(nn_index + row * K + k), f = __ldg(bin_index + row * K + k);
+            size_t ii = ((size_t)b * N + n) * C + ci;
+            atomicAdd(grad_input + ii, g * __ldg(filter + (size_t)f * Co + co));
+            atomicAdd(grad_filter + (size_t)f * Co + co, g * __ldg(input + ii));
+        }
+    }
+}
+
+static ConvPlan plan_bwd(int B, int M, int F, int C, int r)
+{
+    ConvPlan p{0, 0, 0, 0, 0, 0};
+    if (r != 1 && r != 2) return p;
+    int slots = (F + BWD_GROUP - 1) / BWD_GROUP;
+    const int slot_opts[5] = {3, 5, 7, 13, 16};
+    int chosen = 0;
+    for (int i = 0; i < 5; i++) if (slots <= slot_opts[i]) { chosen = slot_opts[i]; break; }
+    if (!chosen) return p;
+    int vec = pick_vec(C);
+    if (chosen * vec * r > 56) vec = (chosen * 2 * r > 56) ? 1 : 2;      // keep the accumulators in registers
+    size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
+    if (smem > SMEM_CAP) return p;
+    p.vec = vec; p.slots = chosen; p.smem = smem;
+    p.chunks = (C + 32 * vec - 1) / (32 * vec);
+    p.threads = (r == 1 && chosen <= 5) ? 1024 : 512;
+    const long long rows = (long long)B * M;
+    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    long long want = sm_count();
+    if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
+    if (want < 1) want = 1;
+    p.grid_x = (int)(nchunks < want ? nchunks : want);
+    while (p.threads > 256 && (long long)p.grid_x * p.chunks * (p.threads / 256) > rows && p.grid_x * p.chunks < sm_count())
+        p.threads >>= 1;
+    return p;
+}
+
+static size_t bwd_partials(const ConvPlan& p) { return (size_t)p.grid_x * (p.threads / 32 / BWD_GROUP); }
+
+}  // namespace sph3d
+
+using namespace sph3d;
+
+extern "C" size_t sph3d_depthwise_conv3d_grad_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
+{
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0) return 0;
+    ConvPlan p = plan_bwd(B, M, F, C, r);
+    if (p.vec == 0) return 0;
+    return bwd_partials(p) * F * C * r * sizeof(float);
+}
+
+extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, int r, int K,
+                                           const int* nn_index, const int* nn_count, const int* bin_index,
+                                           const float* input, const float* filter, const float* grad_output,
+                                           float* grad_input, float* grad_filter,
+                                           void* workspace, size_t workspace_bytes, void* stream)
+{
+    g_last_launch_count = 0;
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0 || !nn_index || !nn_count ||
+        !bin_index || !input || !filter || !grad_output || !grad_input || !grad_filter)
+        return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
+    if (e != cudaSuccess) return (int)e;
+    ConvPlan p = plan_bwd(B, M, F, C, r);
+    if (p.vec == 0) {
+        e = cudaMemsetAsync(grad_filter, 0, sizeof(float) * (size_t)F * C * r, st);
+        if (e != cudaSuccess) return (int)e;
+        size_t total = (size_t)B * M * C * r;
+        size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
+        conv_bwd_generic<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(B, N, M, C, r, K, nn_index, nn_count,
+                                                                              bin_index, input, filter, grad_output,
+                                                                              grad_input, grad_filter);
+        SPH3D_CHECK_LAUNCH();
+        g_last_launch_count = 1;
+        return 0;
+    }
+    const size_t nW = (size_t)F * C * r;
+    const size_t P = bwd_partials(p);
+    if (!workspace || workspace_bytes < P * nW * sizeof(float)) return (int)cudaErrorInvalidValue;
+    dim3 grid(p.grid_x, p.chunks);
+    float* part = (float*)workspace;
+#define LAUNCH_BWD(V, RR, SL)                                                                        \
+    do {                                                                                             \
+        e = set_smem(conv_bwd_kernel<V, RR, SL>, p.smem);                                            \
+        if (e != cudaSuccess) return (int)e;                                                         \
+        conv_bwd_kernel<V, RR, SL><<<grid, p.threads, p.smem, st>>>(B, N, M, F, C, K, nn_index,      \
+                                                                    nn_count, bin_index, input,      \
+                                                                    filter, grad_output, grad_input, \
+                                                                    part);                           \
+    } while (0)
+#define DISPATCH_SLOTS(V, RR)                                                                        \
+    do {                                                                                             \
+        if (p.slots == 3) LAUNCH_BWD(V, RR, 3);                                                      \
+        else if (p.slots == 5) LAUNCH_BWD(V, RR, 5);                                                 \
+        else if (p.slots == 7) LAUNCH_BWD(V, RR, 7);                                                 \
+        else if (p.slots == 13) LAUNCH_BWD(V, RR, 13);                                               \
+        else LAUNCH_BWD(V, RR, 16);                                                                  \
+    } while (0)
+    if (p.vec == 4 && r == 1) DISPATCH_SLOTS(4, 1);
+    else if (p.vec == 4 && r == 2) DISPATCH_SLOTS(4, 2);
+    else if (p.vec == 2 && r == 1) DISPATCH_SLOTS(2, 1);
+    else if (p.vec == 2 && r == 2) DISPATCH_SLOTS(2, 2);
+    else if (p.vec == 1 && r == 1) DISPATCH_SLOTS(1, 1);
+    else DISPATCH_SLOTS(1, 2);
+#undef DISPATCH_SLOTS
+#undef LAUNCH_BWD
+    SPH3D_CHECK_LAUNCH();
+    reduce_partials_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((int)P, nW, part, grad_filter);
+    SPH3D_CHECK_LAUNCH();
+    g_last_launch_count = 2;        // kernels only (the cudaMemsetAsync of grad_input is not counted)
+    return 0;
+}

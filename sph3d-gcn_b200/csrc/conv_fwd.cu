@@ -1,0 +1,204 @@
+// conv_fwd.cu -- depthwise spherical graph convolution, forward, sm_100a.
+//
+// Replaces depthwiseConv3dLauncher (/root/reference/tf_ops/convolution/tf_conv3d_gpu.cu:107-113,
+// kernel :7-29) and the cudaMemset zero fill of tf_conv3d.cpp:90.
+//
+//   out[b,m,c*r+j] = (1/cnt) * sum_{k<cnt} in[b, nn[b,m,k], c] * W[bin[b,m,k], c, j]          (Q9)
+//
+// Design (work unit: rowwarp.cuh).  A warp owns one output point and 32*VEC input channels.  It
+// reads the point's neighbour ids and bin ids ONCE (coalesced, two per lane per 64-edge tile), then
+// walks only the bins that occur in the row (64-bit presence mask from one REDUX.OR): a ballot
+// selects the bin's edges, their feature strips are gathered (one LDG.128 per lane and edge, two in
+// flight per warp) and SUMMED with packed FADD2, and the bin's filter strip -- staged once per
+// persistent CTA in shared memory, conflict-free layout -- is applied once per (row, bin) with
+// FFMA2 instead of once per edge.  This is the segment-weighted-sum form of the op: FMA count drops
+// from E*C*r to (#row-bins)*C*r, shared-memory filter traffic drops by the mean segment length
+// (~4x at K=64, F=33); what remains is the irreducible gather of E*C*4 bytes through L1/L2.
+// Nothing is accumulated in global memory (the reference does a global read-modify-write per edge
+// and channel) and index rows are read once per 32*VEC channels, not once per channel.
+//
+// One persistent CTA of up to 32 warps per SM takes CONTIGUOUS chunks of rows: the reference's
+// "first K in-range points by ascending index" rule (Q4) makes neighbouring rows draw their
+// neighbours from the same low-index set, so a chunk's gathers mostly hit the SM's L1.
+#include "conv_common.cuh"
+#include "../../include/sph3d_b200.h"
+
+namespace sph3d {
+
+int g_last_launch_count = 0;
+
+template <int VEC, int R>
+__global__ void __launch_bounds__(1024, 1)
+conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
+                const int* __restrict__ nn_index, const int* __restrict__ nn_count,
+                const int* __restrict__ bin_index, const float* __restrict__ input,
+                const float* __restrict__ filter, float* __restrict__ output)
+{
+    constexpr int E = VEC * R;
+    using S = SmemStrip<E>;
+    extern __shared__ __align__(16) float smem[];
+    float* Wsh = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cbase = blockIdx.y * 32 * VEC;
+    stage_filter<VEC, R>(Wsh, filter, F, C, cbase);
+    __syncthreads();
+
+    const int c0 = cbase + lane * VEC;
+    const bool active = c0 < C;
+    const long long rows = (long long)B * M;
+    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long rbeg = chunk * ROWS_PER_CHUNK;
+        const long long rend = rbeg + ROWS_PER_CHUNK < rows ? rbeg + ROWS_PER_CHUNK : rows;
+        for (long long row = rbeg + warp; row < rend; row += nwarps) {
+            const int b = (int)(row / M);
+            const int cnt = min(__ldg(nn_count + row), K);
+            const float* inb = input + (size_t)b * N * C + c0;
+            const int* idxrow = nn_index + (size_t)row * K;
+            const int* binrow = bin_index + (size_t)row * K;
+            float acc[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[e] = 0.f;
+
+            for (int kt = 0; kt < cnt; kt += 64) {
+                const int k0 = kt + lane, k1 = kt + 32 + lane;
+                int i0 = 0, b0 = -1, i1 = 0, b1 = -1;
+                if (k0 < cnt) { i0 = __ldg(idxrow + k0); b0 = __ldg(binrow + k0); }
+                if (k1 < cnt) { i1 = __ldg(idxrow + k1); b1 = __ldg(binrow + k1); }
+                auto do_bin = [&](int f) {
+                    const unsigned m0 = __ballot_sync(FULL_MASK, b0 == f);
+                    const unsigned m1 = __ballot_sync(FULL_MASK, b1 == f);
+                    if (!(m0 | m1)) return;
+                    float s[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) s[v] = 0.f;
+                    gather_sum_lean<VEC>(s, m0, i0, inb, C, active);
+                    gather_sum_lean<VEC>(s, m1, i1, inb, C, active);
+                    float w[E];
+                    S::load(w, Wsh + f * S::FLOATS, lane);
+                    if constexpr (E % 2 == 0 && (R == 1 || R == 2)) {
+#pragma unroll
+                        for (int e = 0; e < E; e += 2) {        // FFMA2: (acc[e],acc[e+1]) += (s,s') * (w[e],w[e+1])
+                            float2 a = __ffma2_rn(make_float2(s[e / R], s[(e + 1) / R]), make_float2(w[e], w[e + 1]),
+                                                  make_float2(acc[e], acc[e + 1]));
+                            acc[e] = a.x; acc[e + 1] = a.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[e] = fmaf(s[e / R], w[e], acc[e]);
+                    }
+                };
+                unsigned plo, phi;
+                present_bins(b0, b1, plo, phi);
+                while (plo) do_bin(pop_lowest(plo));
+                while (phi) do_bin(32 + pop_lowest(phi));
+                for (int f = 64; f < F; f++) do_bin(f);
+            }
+            if (active) {
+                const float inv = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+#pragma unroll
+                for (int e = 0; e < E; e++) acc[e] *= inv;
+                float* out = output + (size_t)row * C * R + (size_t)c0 * R;
+                constexpr int VW = strip_vw(E);
+#pragma unroll
+                for (int pl = 0; pl < E / VW; pl++) {
+                    float t[VW];
+#pragma unroll
+                    for (int u = 0; u < VW; u++) t[u] = acc[pl * VW + u];
+                    VecIO<VW>::st(out + pl * VW, t);
+                }
+            }
+        }
+    }
+}
+
+// generic fallback (any r, any F): one thread per output element, parallel over the whole grid
+__global__ void __launch_bounds__(256)
+conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict__ nn_index,
+                 const int* __restrict__ nn_count, const int* __restrict__ bin_index,
+                 const float* __restrict__ input, const float* __restrict__ filter, float* __restrict__ output)
+{
+    const int Co = C * r;
+    const size_t total = (size_t)B * M * Co;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        size_t row = t / Co;
+        int co = (int)(t - row * Co), ci = co / r, b = (int)(row / M);
+        int cnt = min(__ldg(nn_count + row), K);
+        float acc = 0.f;
+        for (int k = 0; k < cnt; k++) {
+            int n = __ldg(nn_index + row * K + k), f = __ldg(bin_index + row * K + k);
+            acc = fmaf(__ldg(input + ((size_t)b * N + n) * C + ci), __ldg(filter + (size_t)f * Co + co), acc);
+        }
+        output[t] = cnt > 0 ? acc / (float)cnt : 0.f;
+    }
+}
+
+static ConvPlan plan_fwd(int B, int M, int F, int C, int r)
+{
+    ConvPlan p{0, 0, 0, 0, 0, 0};
+    if (r != 1 && r != 2) return p;
+    int vec = pick_vec(C);
+    size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
+    while (smem > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
+    if (smem > SMEM_CAP) return p;
+    p.vec = vec; p.smem = smem;
+    p.chunks = (C + 32 * vec - 1) / (32 * vec);
+    const long long rows = (long long)B * M;
+    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    long long want = sm_count();                                   // one persistent 32-warp CTA per SM ...
+    if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;      // ... shared by the channel chunks
+    if (want < 1) want = 1;
+    p.grid_x = (int)(nchunks < want ? nchunks : want);
+    // small problems: fewer warps per CTA so that more SMs get work
+    p.threads = 1024;
+    while (p.threads > 128 && (long long)p.grid_x * p.chunks * (p.threads / 32) > rows && p.grid_x * p.chunks < sm_count())
+        p.threads >>= 1;
+    return p;
+}
+
+}  // namespace sph3d
+
+using namespace sph3d;
+
+extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, int K,
+                                      const int* nn_index, const int* nn_count, const int* bin_index,
+                                      const float* input, const float* filter, float* output, void* stream)
+{
+    g_last_launch_count = 0;
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0 || !nn_index || !nn_count ||
+        !bin_index || !input || !filter || !output)
+        return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvPlan p = plan_fwd(B, M, F, C, r);
+    if (p.vec == 0) {
+        size_t total = (size_t)B * M * C * r;
+        size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
+        conv_fwd_generic<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(B, N, M, C, r, K, nn_index, nn_count,
+                                                                              bin_index, input, filter, output);
+        SPH3D_CHECK_LAUNCH();
+        g_last_launch_count = 1;
+        return 0;
+    }
+    dim3 grid(p.grid_x, p.chunks);
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_FWD(V, RR)                                                                            \
+    do {                                                                                             \
+        e = set_smem(conv_fwd_kernel<V, RR>, p.smem);                                                \
+        if (e != cudaSuccess) return (int)e;                                                         \
+        conv_fwd_kernel<V, RR><<<grid, p.threads, p.smem, st>>>(B, N, M, F, C, K, nn_index, nn_count, \
+                                                                bin_index, input, filter, output);   \
+    } while (0)
+    if (p.vec == 4 && r == 1) LAUNCH_FWD(4, 1);
+    else if (p.vec == 4 && r == 2) LAUNCH_FWD(4, 2);
+    else if (p.vec == 2 && r == 1) LAUNCH_FWD(2, 1);
+    else if (p.vec == 2 && r == 2) LAUNCH_FWD(2, 2);
+    else if (p.vec == 1 && r == 1) LAUNCH_FWD(1, 1);
+    else LAUNCH_FWD(1, 2);
+#undef LAUNCH_FWD
+    SPH3D_CHECK_LAUNCH();
+    g_last_launch_count = 1;
+    return 0;
+}
+
+extern "C" int sph3d_abi_version(void) { return SPH3D_B200_ABI_VERSION; }
+extern "C" int sph3d_last_launch_count(void) { return g_last_launch_count; }

@@ -192,7 +192,7 @@ def test_depthwise_conv3d_backward(case, pkg, oracle, ref):
     assert_close(A(Wt.grad), tf, 1e-5, case[0] + " grad_filter vs fp64 oracle")
     # grad_filter is reduced in a fixed order: deterministic run to run
     gi2, gf2 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
-    if W.shape[2] in (1, 2):                 # (the any-r fallback uses float atomics, like the reference)
+    if W.shape[2] in (1, 2) and W.shape[0] <= 128:   # (the any-r / huge-F fallback uses float atomics, like the reference)
         assert_equal(A(gf2), A(Wt.grad), "grad_filter determinism")
     if ref is not None:
         ri, rf = ref.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
