@@ -7,15 +7,16 @@
 //   grad_input [b, nn[b,m,k], c]  += sum_j gO[b,m,c*r+j] * W[bin[b,m,k], c, j] / cnt
 //   grad_filter[bin[b,m,k], c, j] +=       gO[b,m,c*r+j] * in[b, nn[b,m,k], c] / cnt
 //
-// ONE fused pass.  A group of 8 warps shares one output row; warp w of the group OWNS the filter
-// bins f = w, w+8, w+16, ... (SLOTS of them).  For each of its bins that occurs in the row (ballot) it
+// ONE fused pass.  A group of G warps (G = 1, 2, 4 or 8, the smallest that keeps the accumulators in
+// registers) shares one output row; warp w of the group OWNS the filter bins f = w, w+G, w+2G, ...
+// (SLOTS of them).  For each of its bins that occurs in the row (ballot) it
 //   - forms d = sum_j g*W[f] once (filter strip from shared memory),
 //   - walks the bin's edges: gathers the input strip (LDG.128), adds it to a running sum (FADD2) and
 //     scatters d into grad_input with ONE 16-byte vector reduction per lane (REDG.ADD.F32x4),
 //   - folds g * sum(in) into its REGISTER accumulator for that bin.
 // Because bins are owned, the filter gradient needs no atomics and no shared-memory accumulation at
 // all: every warp keeps SLOTS x (VEC*R) accumulators in registers for the whole kernel and writes
-// them once, as a per-CTA partial that a second tiny kernel sums in a fixed order (deterministic
+// them once, as a per-group partial that a second tiny kernel sums in a fixed order (deterministic
 // grad_filter).  The reference instead issues E*C*r shared-memory float atomics per 48 KB filter
 // window and re-runs the whole pass ceil(F*C*r/12288) times (Q13/Q14).
 #include "conv_common.cuh"
@@ -23,11 +24,17 @@
 
 namespace sph3d {
 
-constexpr int BWD_GROUP = 8;     // warps sharing one row; warp-in-group = owner of bins w, w+8, ...
+constexpr int BWD_THREADS = 512;
+
+template <int VEC>
+__device__ __forceinline__ void red_strip(char* __restrict__ base, unsigned off, const float (&d)[VEC])
+{
+    VecIO<VEC>::red(reinterpret_cast<float*>(base + off), d);
+}
 
 template <int VEC, int R, int SLOTS>
-__global__ void __launch_bounds__((R == 1 && SLOTS <= 5) ? 1024 : 512, 1)
-conv_bwd_kernel(int B, int N, int M, int F, int C, int K,
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+conv_bwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K, int G,
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                 const int* __restrict__ bin_index, const float* __restrict__ input,
                 const float* __restrict__ filter, const float* __restrict__ grad_output,
@@ -38,99 +45,106 @@ conv_bwd_kernel(int B, int N, int M, int F, int C, int K,
     extern __shared__ __align__(16) float smem[];
     float* Wsh = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wig = warp % BWD_GROUP, group = warp / BWD_GROUP, ngroups = (blockDim.x >> 5) / BWD_GROUP;
+    const int wig = warp % G, group = warp / G, ngroups = (blockDim.x >> 5) / G;
     const int cbase = blockIdx.y * 32 * VEC;
     stage_filter<VEC, R>(Wsh, filter, F, C, cbase);
     __syncthreads();
 
     const int c0 = cbase + lane * VEC;
     const bool active = c0 < C;
+    const int c0ld = active ? c0 : 0;
+    const unsigned strideB = (unsigned)C * 4u;
+    const size_t cloudB = (size_t)N * C * 4;
+    const float* wlane = Wsh + S::offset(0, lane) + wig * S::FLOATS;      // strip of my first bin
+    const int wstep = G * S::FLOATS;
     float acc[SLOTS][E];
 #pragma unroll
     for (int s = 0; s < SLOTS; s++)
 #pragma unroll
         for (int e = 0; e < E; e++) acc[s][e] = 0.f;
 
-    const long long rows = (long long)B * M;
-    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
-    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const long long rbeg = chunk * ROWS_PER_CHUNK;
-        const long long rend = rbeg + ROWS_PER_CHUNK < rows ? rbeg + ROWS_PER_CHUNK : rows;
-        for (long long row = rbeg + group; row < rend; row += ngroups) {
-            const int b = (int)(row / M);
+    const unsigned nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const unsigned rbeg = chunk * ROWS_PER_CHUNK;
+        const unsigned rend = min(rbeg + ROWS_PER_CHUNK, rows);
+        unsigned row = rbeg + group;
+        if (row >= rend) continue;
+        RowCursor cur;
+        cur.init(row, M);
+        for (; row < rend; row += ngroups, cur.advance(ngroups, M)) {
             const int cnt = min(__ldg(nn_count + row), K);
             if (cnt <= 0) continue;
-            const float* inb = input + (size_t)b * N * C + c0;
-            float* gib = grad_input + (size_t)b * N * C + c0;
+            const char* inb = reinterpret_cast<const char*>(input) + cur.b * cloudB + (size_t)c0ld * 4;
+            char* gib = reinterpret_cast<char*>(grad_input) + cur.b * cloudB + (size_t)c0ld * 4;
             const int* idxrow = nn_index + (size_t)row * K;
             const int* binrow = bin_index + (size_t)row * K;
             float g[E];
             {
                 const float inv = 1.0f / (float)cnt;
-                const float* go = grad_output + (size_t)row * C * R + (size_t)c0 * R;
+                const float* go = grad_output + ((size_t)row * C + c0ld) * R;
                 constexpr int VW = strip_vw(E);
 #pragma unroll
                 for (int pl = 0; pl < E / VW; pl++) {
                     float t[VW];
-                    VecIO<VW>::ld(t, go + pl * VW, active);
+                    VecIO<VW>::ld(t, go + pl * VW, true);
 #pragma unroll
-                    for (int u = 0; u < VW; u++) g[pl * VW + u] = t[u] * inv;
+                    for (int u = 0; u < VW; u++) g[pl * VW + u] = active ? t[u] * inv : 0.f;
                 }
             }
             for (int kt = 0; kt < cnt; kt += 64) {
                 const int k0 = kt + lane, k1 = kt + 32 + lane;
-                int i0 = 0, b0 = -1, i1 = 0, b1 = -1;
-                if (k0 < cnt) { i0 = __ldg(idxrow + k0); b0 = __ldg(binrow + k0); }
-                if (k1 < cnt) { i1 = __ldg(idxrow + k1); b1 = __ldg(binrow + k1); }
+                unsigned o0 = 0, o1 = 0;
+                int b0 = -1, b1 = -1;
+                if (k0 < cnt) { o0 = (unsigned)__ldg(idxrow + k0) * strideB; b0 = __ldg(binrow + k0); }
+                if (k1 < cnt) { o1 = (unsigned)__ldg(idxrow + k1) * strideB; b1 = __ldg(binrow + k1); }
+                // bins of mine that occur in this tile: bit s <-> bin wig + s*G
+                int f = wig;
 #pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    const int f = wig + s * BWD_GROUP;
-                    if (f < F) {
-                        unsigned m0 = __ballot_sync(FULL_MASK, b0 == f);
-                        unsigned m1 = __ballot_sync(FULL_MASK, b1 == f);
-                        if (m0 | m1) {
-                            float w[E];
-                            S::load(w, Wsh + f * S::FLOATS, lane);
-                            float d[VEC], sv[VEC];
+                for (int s = 0; s < SLOTS; s++, f += G) {
+                    const unsigned m0 = __ballot_sync(FULL_MASK, b0 == f);
+                    const unsigned m1 = __ballot_sync(FULL_MASK, b1 == f);
+                    if (m0 | m1) {                      // (f >= F never matches: bins are < F)
+                        float w[E];
+                        S::load(w, wlane + s * wstep, 0);
+                        float d[VEC], sv[VEC];
 #pragma unroll
-                            for (int v = 0; v < VEC; v++) {
-                                float t = 0.f;
+                        for (int v = 0; v < VEC; v++) {
+                            float t = 0.f;
 #pragma unroll
-                                for (int j = 0; j < R; j++) t = fmaf(g[v * R + j], w[v * R + j], t);
-                                d[v] = t; sv[v] = 0.f;
-                            }
-                            auto edges = [&](unsigned m, int myidx) {
-                                while (m) {
-                                    const int n0 = __shfl_sync(FULL_MASK, myidx, pop_highest(m));
-                                    float v0[VEC];
-                                    VecIO<VEC>::ld(v0, inb + (size_t)n0 * C, active);
-                                    if (active) VecIO<VEC>::red(gib + (size_t)n0 * C, d);
-                                    if (m) {
-                                        const int n1 = __shfl_sync(FULL_MASK, myidx, pop_highest(m));
-                                        float v1[VEC];
-                                        VecIO<VEC>::ld(v1, inb + (size_t)n1 * C, active);
-                                        if (active) VecIO<VEC>::red(gib + (size_t)n1 * C, d);
-                                        strip_add<VEC>(sv, v1);
-                                    }
-                                    strip_add<VEC>(sv, v0);
-                                }
-                            };
-                            edges(m0, i0);
-                            edges(m1, i1);
-#pragma unroll
-                            for (int e = 0; e < E; e++) acc[s][e] = fmaf(g[e], sv[e / R], acc[s][e]);
+                            for (int j = 0; j < R; j++) t = fmaf(g[v * R + j], w[v * R + j], t);
+                            d[v] = t; sv[v] = 0.f;
                         }
+                        auto edges = [&](unsigned m, unsigned myoff) {
+                            while (m) {
+                                const unsigned q0 = __shfl_sync(FULL_MASK, myoff, pop_highest(m));
+                                float v0[VEC];
+                                ld_strip<VEC>(v0, inb, q0);
+                                if (active) red_strip<VEC>(gib, q0, d);
+                                if (m) {
+                                    const unsigned q1 = __shfl_sync(FULL_MASK, myoff, pop_highest(m));
+                                    float v1[VEC];
+                                    ld_strip<VEC>(v1, inb, q1);
+                                    if (active) red_strip<VEC>(gib, q1, d);
+                                    strip_add<VEC>(sv, v1);
+                                }
+                                strip_add<VEC>(sv, v0);
+                            }
+                        };
+                        edges(m0, o0);
+                        edges(m1, o1);
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[s][e] = fmaf(g[e], sv[e / R], acc[s][e]);
                     }
                 }
             }
         }
     }
-    // per-CTA partial [blockIdx.x][group][f][c][j]: each (f, c-chunk) is written by exactly one warp
+    // partial [blockIdx.x][group][f][c][j]: each (f, c-chunk) is written by exactly one warp of the group
     float* part = gw_partial + ((size_t)blockIdx.x * ngroups + group) * F * C * R;
     if (active) {
+        int f = wig;
 #pragma unroll
-        for (int s = 0; s < SLOTS; s++) {
-            const int f = wig + s * BWD_GROUP;
+        for (int s = 0; s < SLOTS; s++, f += G) {
             if (f < F) {
                 float* dst = part + ((size_t)f * C + c0) * R;
                 constexpr int VW = strip_vw(E);
@@ -161,7 +175,7 @@ reduce_partials_kernel(int P, size_t n, const float* __restrict__ part, float* _
     }
 }
 
-// generic fallback (any r, any F): float atomics, like the reference but parallel over the whole grid
+// generic fallback (any r, any F, any size): float atomics, like the reference but grid-parallel
 __global__ void __launch_bounds__(256)
 conv_bwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict__ nn_index,
                  const int* __restrict__ nn_count, const int* __restrict__ bin_index,
@@ -186,34 +200,43 @@ conv_bwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict
     }
 }
 
-static ConvPlan plan_bwd(int B, int M, int F, int C, int r)
+// plan: vec in {4,2,1}, SLOTS in {9,17}, G in {1,2,4,8} with G*SLOTS >= F and SLOTS*vec*r <= 72 registers
+static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
 {
     ConvPlan p{0, 0, 0, 0, 0, 0};
-    if (r != 1 && r != 2) return p;
-    int slots = (F + BWD_GROUP - 1) / BWD_GROUP;
-    const int slot_opts[5] = {3, 5, 7, 13, 16};
-    int chosen = 0;
-    for (int i = 0; i < 5; i++) if (slots <= slot_opts[i]) { chosen = slot_opts[i]; break; }
-    if (!chosen) return p;
-    int vec = pick_vec(C);
-    if (chosen * vec * r > 56) vec = (chosen * 2 * r > 56) ? 1 : 2;      // keep the accumulators in registers
+    *G_out = 0;
+    if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 136) return p;
+    int vec = pick_vec(C), slots = 0, G = 0;
+    for (; vec >= 1 && !G; vec = (vec > 1 ? vec >> 1 : 0)) {
+        const int slot_opts[2] = {17, 9};
+        for (int i = 0; i < 2 && !G; i++) {
+            if (slot_opts[i] * vec * r > 72) continue;
+            for (int g = 1; g <= 8; g <<= 1)
+                if (g * slot_opts[i] >= F) { G = g; slots = slot_opts[i]; break; }
+        }
+        if (G) break;
+        if (vec == 1) break;
+    }
+    if (!G) return p;
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
     if (smem > SMEM_CAP) return p;
-    p.vec = vec; p.slots = chosen; p.smem = smem;
+    p.vec = vec; p.slots = slots; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
-    p.threads = (r == 1 && chosen <= 5) ? 1024 : 512;
+    p.threads = BWD_THREADS;
     const long long rows = (long long)B * M;
     const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
     long long want = sm_count();
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
     if (want < 1) want = 1;
     p.grid_x = (int)(nchunks < want ? nchunks : want);
-    while (p.threads > 256 && (long long)p.grid_x * p.chunks * (p.threads / 256) > rows && p.grid_x * p.chunks < sm_count())
+    while (p.threads > 32 * G && p.threads > 64 &&
+           (long long)p.grid_x * p.chunks * (p.threads / (32 * G)) > rows && p.grid_x * p.chunks < sm_count())
         p.threads >>= 1;
+    *G_out = G;
     return p;
 }
 
-static size_t bwd_partials(const ConvPlan& p) { return (size_t)p.grid_x * (p.threads / 32 / BWD_GROUP); }
+static size_t bwd_partials(const ConvPlan& p, int G) { return (size_t)p.grid_x * (p.threads / 32 / G); }
 
 }  // namespace sph3d
 
@@ -222,9 +245,10 @@ using namespace sph3d;
 extern "C" size_t sph3d_depthwise_conv3d_grad_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
 {
     if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0) return 0;
-    ConvPlan p = plan_bwd(B, M, F, C, r);
+    int G = 0;
+    ConvPlan p = plan_bwd(B, N, M, F, C, r, &G);
     if (p.vec == 0) return 0;
-    return bwd_partials(p) * F * C * r * sizeof(float);
+    return bwd_partials(p, G) * F * C * r * sizeof(float);
 }
 
 extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, int r, int K,
@@ -240,7 +264,8 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
     if (e != cudaSuccess) return (int)e;
-    ConvPlan p = plan_bwd(B, M, F, C, r);
+    int G = 0;
+    ConvPlan p = plan_bwd(B, N, M, F, C, r, &G);
     if (p.vec == 0) {
         e = cudaMemsetAsync(grad_filter, 0, sizeof(float) * (size_t)F * C * r, st);
         if (e != cudaSuccess) return (int)e;
@@ -254,29 +279,27 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
         return 0;
     }
     const size_t nW = (size_t)F * C * r;
-    const size_t P = bwd_partials(p);
+    const size_t P = bwd_partials(p, G);
     if (!workspace || workspace_bytes < P * nW * sizeof(float)) return (int)cudaErrorInvalidValue;
     dim3 grid(p.grid_x, p.chunks);
+    const unsigned rows = (unsigned)((long long)B * M);
     float* part = (float*)workspace;
 #define LAUNCH_BWD(V, RR, SL)                                                                        \
     do {                                                                                             \
         e = set_smem(conv_bwd_kernel<V, RR, SL>, p.smem);                                            \
         if (e != cudaSuccess) return (int)e;                                                         \
-        conv_bwd_kernel<V, RR, SL><<<grid, p.threads, p.smem, st>>>(B, N, M, F, C, K, nn_index,      \
-                                                                    nn_count, bin_index, input,      \
-                                                                    filter, grad_output, grad_input, \
-                                                                    part);                           \
+        conv_bwd_kernel<V, RR, SL><<<grid, p.threads, p.smem, st>>>(rows, N, (unsigned)M, F, C, K,   \
+                                                                    G, nn_index, nn_count,           \
+                                                                    bin_index, input, filter,        \
+                                                                    grad_output, grad_input, part);  \
     } while (0)
 #define DISPATCH_SLOTS(V, RR)                                                                        \
     do {                                                                                             \
-        if (p.slots == 3) LAUNCH_BWD(V, RR, 3);                                                      \
-        else if (p.slots == 5) LAUNCH_BWD(V, RR, 5);                                                 \
-        else if (p.slots == 7) LAUNCH_BWD(V, RR, 7);                                                 \
-        else if (p.slots == 13) LAUNCH_BWD(V, RR, 13);                                               \
-        else LAUNCH_BWD(V, RR, 16);                                                                  \
+        if (p.slots == 9) LAUNCH_BWD(V, RR, 9);                                                      \
+        else LAUNCH_BWD(V, RR, 17);                                                                  \
     } while (0)
     if (p.vec == 4 && r == 1) DISPATCH_SLOTS(4, 1);
-    else if (p.vec == 4 && r == 2) DISPATCH_SLOTS(4, 2);
+    else if (p.vec == 4 && r == 2) LAUNCH_BWD(4, 2, 9);
     else if (p.vec == 2 && r == 1) DISPATCH_SLOTS(2, 1);
     else if (p.vec == 2 && r == 2) DISPATCH_SLOTS(2, 2);
     else if (p.vec == 1 && r == 1) DISPATCH_SLOTS(1, 1);

@@ -1,4 +1,9 @@
 // conv_common.cuh -- pieces shared by the forward and backward convolution kernels.
+//
+// Index arithmetic in the hot loops is 32-bit on purpose: a neighbour id is turned ONCE per row into a
+// byte offset inside its cloud (id * C * 4, host-checked to fit 32 bits), shuffles then broadcast
+// ready-made offsets and an address is one 64-bit add.  Row/cloud bookkeeping is incremental (no
+// 64-bit divisions in device code).
 #pragma once
 #include "rowwarp.cuh"
 
@@ -18,7 +23,23 @@ __device__ __forceinline__ void stage_filter(float* Wsh, const float* __restrict
     }
 }
 
-// s += v, with Blackwell's packed fp32x2 adds (FADD2) where the strip is wide enough
+// unconditional strip load at byte offset `off` from `base` (callers clamp idle lanes to a valid strip)
+template <int VEC>
+__device__ __forceinline__ void ld_strip(float (&v)[VEC], const char* __restrict__ base, unsigned off)
+{
+    const float* p = reinterpret_cast<const float*>(base + off);
+    if constexpr (VEC == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+// s += v, with Blackwell's packed fp32x2 add (FADD2) where the strip is wide enough
 template <int VEC>
 __device__ __forceinline__ void strip_add(float (&s)[VEC], const float (&v)[VEC])
 {
@@ -34,7 +55,7 @@ __device__ __forceinline__ void strip_add(float (&s)[VEC], const float (&v)[VEC]
     }
 }
 
-// highest set bit of a non-zero, warp-uniform mask; clears it (FLO + SHF + LOP: cheaper than ffs)
+// highest set bit of a non-zero, warp-uniform mask; clears it (FLO + SHF + LOP)
 __device__ __forceinline__ int pop_highest(unsigned& m)
 {
     int b = 31 - __clz(m);
@@ -42,25 +63,43 @@ __device__ __forceinline__ int pop_highest(unsigned& m)
     return b;
 }
 
-// Sum the feature strips of the neighbours selected by the warp-uniform mask m (bit k <-> the id held
-// by lane k in `myidx`).  Two independent gathers per trip, every branch is warp-uniform, no padding.
+// Sum the feature strips of the edges selected by the warp-uniform mask m.  Bit k <-> the byte offset
+// held by lane k in `myoff`.  Up to four independent gathers in flight; every branch is warp-uniform;
+// no padding work.
 template <int VEC>
-__device__ __forceinline__ void gather_sum_lean(float (&s)[VEC], unsigned m, int myidx,
-                                                const float* __restrict__ inb, int C, bool active)
+__device__ __forceinline__ void gather_sum_lean(float (&s)[VEC], unsigned m, unsigned myoff,
+                                                const char* __restrict__ inb)
 {
     while (m) {
-        const int n0 = __shfl_sync(FULL_MASK, myidx, pop_highest(m));
-        float v0[VEC];
-        VecIO<VEC>::ld(v0, inb + (size_t)n0 * C, active);
+        float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+        ld_strip<VEC>(v0, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
         if (m) {
-            const int n1 = __shfl_sync(FULL_MASK, myidx, pop_highest(m));
-            float v1[VEC];
-            VecIO<VEC>::ld(v1, inb + (size_t)n1 * C, active);
+            ld_strip<VEC>(v1, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
+            if (m) {
+                ld_strip<VEC>(v2, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
+                if (m) {
+                    ld_strip<VEC>(v3, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
+                    strip_add<VEC>(s, v3);
+                }
+                strip_add<VEC>(s, v2);
+            }
             strip_add<VEC>(s, v1);
         }
         strip_add<VEC>(s, v0);
     }
 }
+
+// Incremental (cloud, point) bookkeeping for a warp that visits rows row0, row0+step, ... of a
+// contiguous chunk: avoids a division per row.
+struct RowCursor {
+    unsigned b, m;
+    __device__ __forceinline__ void init(unsigned row, unsigned M) { b = row / M; m = row - b * M; }
+    __device__ __forceinline__ void advance(unsigned step, unsigned M)
+    {
+        m += step;
+        while (m >= M) { m -= M; b++; }
+    }
+};
 
 struct ConvPlan {
     int vec;          // 4 / 2 / 1, 0 = generic fallback
@@ -73,6 +112,13 @@ struct ConvPlan {
 
 static inline int pick_vec(int C) { return (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1); }
 static const size_t SMEM_CAP = 227 * 1024;
+
+// the lean kernels use 32-bit row ids and 32-bit byte offsets inside a cloud
+static inline bool fits_32bit(int B, int N, int M, int C, int r)
+{
+    return (long long)B * M < (1LL << 31) && (long long)N * C * 4 < (1LL << 32) &&
+           (long long)M * C * r * 4 < (1LL << 40);
+}
 
 // rows are handed to CTAs in contiguous chunks so that the warps sharing an SM's L1 work on
 // neighbouring rows (the "first K by index" rule makes neighbouring rows share most neighbours)

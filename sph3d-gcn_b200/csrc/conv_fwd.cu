@@ -8,8 +8,8 @@
 // Design (work unit: rowwarp.cuh).  A warp owns one output point and 32*VEC input channels.  It
 // reads the point's neighbour ids and bin ids ONCE (coalesced, two per lane per 64-edge tile), then
 // walks only the bins that occur in the row (64-bit presence mask from one REDUX.OR): a ballot
-// selects the bin's edges, their feature strips are gathered (one LDG.128 per lane and edge, two in
-// flight per warp) and SUMMED with packed FADD2, and the bin's filter strip -- staged once per
+// selects the bin's edges, their feature strips are gathered (one LDG.128 per lane and edge, up to
+// four in flight per warp) and SUMMED with packed FADD2, and the bin's filter strip -- staged once per
 // persistent CTA in shared memory, conflict-free layout -- is applied once per (row, bin) with
 // FFMA2 instead of once per edge.  This is the segment-weighted-sum form of the op: FMA count drops
 // from E*C*r to (#row-bins)*C*r, shared-memory filter traffic drops by the mean segment length
@@ -29,7 +29,7 @@ int g_last_launch_count = 0;
 
 template <int VEC, int R>
 __global__ void __launch_bounds__(1024, 1)
-conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
+conv_fwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K,
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                 const int* __restrict__ bin_index, const float* __restrict__ input,
                 const float* __restrict__ filter, float* __restrict__ output)
@@ -45,15 +45,22 @@ conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
 
     const int c0 = cbase + lane * VEC;
     const bool active = c0 < C;
-    const long long rows = (long long)B * M;
-    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
-    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const long long rbeg = chunk * ROWS_PER_CHUNK;
-        const long long rend = rbeg + ROWS_PER_CHUNK < rows ? rbeg + ROWS_PER_CHUNK : rows;
-        for (long long row = rbeg + warp; row < rend; row += nwarps) {
-            const int b = (int)(row / M);
+    const int c0ld = active ? c0 : 0;                      // idle lanes load a valid strip, never store
+    const unsigned strideB = (unsigned)C * 4u;
+    const size_t cloudB = (size_t)N * C * 4;
+    const float* wlane = Wsh + S::offset(0, lane);
+    const unsigned nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+
+    for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const unsigned rbeg = chunk * ROWS_PER_CHUNK;
+        const unsigned rend = min(rbeg + ROWS_PER_CHUNK, rows);
+        unsigned row = rbeg + warp;
+        if (row >= rend) continue;
+        RowCursor cur;
+        cur.init(row, M);
+        for (; row < rend; row += nwarps, cur.advance(nwarps, M)) {
             const int cnt = min(__ldg(nn_count + row), K);
-            const float* inb = input + (size_t)b * N * C + c0;
+            const char* inb = reinterpret_cast<const char*>(input) + cur.b * cloudB + (size_t)c0ld * 4;
             const int* idxrow = nn_index + (size_t)row * K;
             const int* binrow = bin_index + (size_t)row * K;
             float acc[E];
@@ -62,9 +69,10 @@ conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
 
             for (int kt = 0; kt < cnt; kt += 64) {
                 const int k0 = kt + lane, k1 = kt + 32 + lane;
-                int i0 = 0, b0 = -1, i1 = 0, b1 = -1;
-                if (k0 < cnt) { i0 = __ldg(idxrow + k0); b0 = __ldg(binrow + k0); }
-                if (k1 < cnt) { i1 = __ldg(idxrow + k1); b1 = __ldg(binrow + k1); }
+                unsigned o0 = 0, o1 = 0;
+                int b0 = -1, b1 = -1;
+                if (k0 < cnt) { o0 = (unsigned)__ldg(idxrow + k0) * strideB; b0 = __ldg(binrow + k0); }
+                if (k1 < cnt) { o1 = (unsigned)__ldg(idxrow + k1) * strideB; b1 = __ldg(binrow + k1); }
                 auto do_bin = [&](int f) {
                     const unsigned m0 = __ballot_sync(FULL_MASK, b0 == f);
                     const unsigned m1 = __ballot_sync(FULL_MASK, b1 == f);
@@ -72,11 +80,11 @@ conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
                     float s[VEC];
 #pragma unroll
                     for (int v = 0; v < VEC; v++) s[v] = 0.f;
-                    gather_sum_lean<VEC>(s, m0, i0, inb, C, active);
-                    gather_sum_lean<VEC>(s, m1, i1, inb, C, active);
+                    gather_sum_lean<VEC>(s, m0, o0, inb);
+                    gather_sum_lean<VEC>(s, m1, o1, inb);
                     float w[E];
-                    S::load(w, Wsh + f * S::FLOATS, lane);
-                    if constexpr (E % 2 == 0 && (R == 1 || R == 2)) {
+                    S::load(w, wlane + f * S::FLOATS, 0);
+                    if constexpr (E % 2 == 0) {
 #pragma unroll
                         for (int e = 0; e < E; e += 2) {        // FFMA2: (acc[e],acc[e+1]) += (s,s') * (w[e],w[e+1])
                             float2 a = __ffma2_rn(make_float2(s[e / R], s[(e + 1) / R]), make_float2(w[e], w[e + 1]),
@@ -98,7 +106,7 @@ conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
                 const float inv = cnt > 0 ? 1.0f / (float)cnt : 0.f;
 #pragma unroll
                 for (int e = 0; e < E; e++) acc[e] *= inv;
-                float* out = output + (size_t)row * C * R + (size_t)c0 * R;
+                float* out = output + ((size_t)row * C + c0) * R;
                 constexpr int VW = strip_vw(E);
 #pragma unroll
                 for (int pl = 0; pl < E / VW; pl++) {
@@ -112,7 +120,7 @@ conv_fwd_kernel(int B, int N, int M, int F, int C, int K,
     }
 }
 
-// generic fallback (any r, any F): one thread per output element, parallel over the whole grid
+// generic fallback (any r, any F, any size): one thread per output element
 __global__ void __launch_bounds__(256)
 conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict__ nn_index,
                  const int* __restrict__ nn_count, const int* __restrict__ bin_index,
@@ -133,10 +141,10 @@ conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict
     }
 }
 
-static ConvPlan plan_fwd(int B, int M, int F, int C, int r)
+static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
 {
     ConvPlan p{0, 0, 0, 0, 0, 0};
-    if (r != 1 && r != 2) return p;
+    if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r)) return p;
     int vec = pick_vec(C);
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
     while (smem > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
@@ -169,7 +177,7 @@ extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, 
         !bin_index || !input || !filter || !output)
         return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
-    ConvPlan p = plan_fwd(B, M, F, C, r);
+    ConvPlan p = plan_fwd(B, N, M, F, C, r);
     if (p.vec == 0) {
         size_t total = (size_t)B * M * C * r;
         size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
@@ -180,13 +188,15 @@ extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, 
         return 0;
     }
     dim3 grid(p.grid_x, p.chunks);
+    const unsigned rows = (unsigned)((long long)B * M);
     cudaError_t e = cudaSuccess;
 #define LAUNCH_FWD(V, RR)                                                                            \
     do {                                                                                             \
         e = set_smem(conv_fwd_kernel<V, RR>, p.smem);                                                \
         if (e != cudaSuccess) return (int)e;                                                         \
-        conv_fwd_kernel<V, RR><<<grid, p.threads, p.smem, st>>>(B, N, M, F, C, K, nn_index, nn_count, \
-                                                                bin_index, input, filter, output);   \
+        conv_fwd_kernel<V, RR><<<grid, p.threads, p.smem, st>>>(rows, N, (unsigned)M, F, C, K,       \
+                                                                nn_index, nn_count, bin_index,       \
+                                                                input, filter, output);              \
     } while (0)
     if (p.vec == 4 && r == 1) LAUNCH_FWD(4, 1);
     else if (p.vec == 4 && r == 2) LAUNCH_FWD(4, 2);
