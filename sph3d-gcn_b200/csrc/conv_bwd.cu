@@ -17,7 +17,11 @@
 // Because bins are owned, the filter gradient needs no atomics and no shared-memory accumulation at
 // all: every warp keeps SLOTS x (VEC*R) accumulators in registers for the whole kernel and writes
 // them once, as a per-group partial that a second tiny kernel sums in a fixed order (deterministic
-// grad_filter).  The reference instead issues E*C*r shared-memory float atomics per 48 KB filter
+// grad_filter).  Measured alternatives that lost on B200 (profiles/): sorting the tile by bin first
+// (as the forward kernel does) costs more than it saves when two warps share a row, and replacing the
+// vector reductions by TMA bulk reductions (UBLKRED.G.S.ADD.F32, one 512-byte cp.reduce.async.bulk per
+// edge) is 2.4x slower: the TMA unit sustains only about one small bulk op per ~80 cycles per SM.
+// The reference instead issues E*C*r shared-memory float atomics per 48 KB filter
 // window and re-runs the whole pass ceil(F*C*r/12288) times (Q13/Q14).
 #include "conv_common.cuh"
 #include "../../include/sph3d_b200.h"
@@ -34,7 +38,7 @@ __device__ __forceinline__ void red_strip(char* __restrict__ base, unsigned off,
 
 template <int VEC, int R, int SLOTS>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-conv_bwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K, int G,
+conv_bwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, int K, int G,
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                 const int* __restrict__ bin_index, const float* __restrict__ input,
                 const float* __restrict__ filter, const float* __restrict__ grad_output,
@@ -63,10 +67,10 @@ conv_bwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K, int G,
 #pragma unroll
         for (int e = 0; e < E; e++) acc[s][e] = 0.f;
 
-    const unsigned nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    const unsigned nchunks = (rows + rpc - 1) / rpc;
     for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const unsigned rbeg = chunk * ROWS_PER_CHUNK;
-        const unsigned rend = min(rbeg + ROWS_PER_CHUNK, rows);
+        const unsigned rbeg = chunk * rpc;
+        const unsigned rend = min(rbeg + rpc, rows);
         unsigned row = rbeg + group;
         if (row >= rend) continue;
         RowCursor cur;
@@ -218,13 +222,19 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
         if (vec == 1) break;
     }
     if (!G) return p;
+    {   // sweep knob: a larger group (fewer bins per warp) is always legal
+        int g_env = tune_int("SPH3D_BWD_G", G);
+        if ((g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) && g_env > G) G = g_env;
+    }
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
     if (smem > SMEM_CAP) return p;
     p.vec = vec; p.slots = slots; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
-    p.threads = BWD_THREADS;
+    p.threads = tune_int("SPH3D_BWD_THREADS", BWD_THREADS);
+    if (p.threads > BWD_THREADS || p.threads % (32 * G)) p.threads = BWD_THREADS;
     const long long rows = (long long)B * M;
-    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    const int rpc = rows_per_chunk();
+    const long long nchunks = (rows + rpc - 1) / rpc;
     long long want = sm_count();
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
     if (want < 1) want = 1;
@@ -283,12 +293,13 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
     if (!workspace || workspace_bytes < P * nW * sizeof(float)) return (int)cudaErrorInvalidValue;
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * M);
+    const unsigned rpc = (unsigned)rows_per_chunk();
     float* part = (float*)workspace;
 #define LAUNCH_BWD(V, RR, SL)                                                                        \
     do {                                                                                             \
         e = set_smem(conv_bwd_kernel<V, RR, SL>, p.smem);                                            \
         if (e != cudaSuccess) return (int)e;                                                         \
-        conv_bwd_kernel<V, RR, SL><<<grid, p.threads, p.smem, st>>>(rows, N, (unsigned)M, F, C, K,   \
+        conv_bwd_kernel<V, RR, SL><<<grid, p.threads, p.smem, st>>>(rows, rpc, N, (unsigned)M, F, C, K, \
                                                                     G, nn_index, nn_count,           \
                                                                     bin_index, input, filter,        \
                                                                     grad_output, grad_input, part);  \

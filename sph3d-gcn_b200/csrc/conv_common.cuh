@@ -5,6 +5,7 @@
 // ready-made offsets and an address is one 64-bit add.  Row/cloud bookkeeping is incremental (no
 // 64-bit divisions in device code).
 #pragma once
+#include <cstdlib>
 #include "rowwarp.cuh"
 
 namespace sph3d {
@@ -101,6 +102,64 @@ struct RowCursor {
     }
 };
 
+// -------------------------------------------------------------------------------------------------
+// Warp-level counting sort of one 64-edge tile by filter bin.
+//
+// Lane l holds edge l (o0, b0) and edge 32+l (o1, b1); b = -1 marks "no edge".  After the call the
+// warp's shared arrays hold the tile grouped by bin, ascending bin, original k order inside a bin:
+//     sOff [p]  byte offset of the p-th edge's neighbour row,        p < n_edges
+//     sCode[p]  (bin << 1) | last     last = 1 on the final edge of a bin's segment
+//     hA[f]     start position of bin f (exclusive prefix over ALL bins, hA[FP] = n_edges)
+// Deterministic (ranks come from MATCH.ANY lane masks, not from atomics).  ~85 instructions per tile,
+// which buys a flat, counted, branch-light gather loop instead of per-bin mask walking.
+// FP = number of bins rounded up to a multiple of 32 (<= 128); hA has FP+1 ints, hB has FP ints.
+__device__ __forceinline__ void sort_tile_by_bin(unsigned o0, int b0, unsigned o1, int b1, int FP, int lane,
+                                                 int* __restrict__ hA, int* __restrict__ hB,
+                                                 unsigned* __restrict__ sOff, int* __restrict__ sCode)
+{
+    for (int f = lane; f < FP; f += 32) { hA[f] = 0; hB[f] = 0; }
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned p0 = __match_any_sync(FULL_MASK, b0), p1 = __match_any_sync(FULL_MASK, b1);
+    const int r0 = __popc(p0 & lt), r1 = __popc(p1 & lt);
+    const int n0 = __popc(p0), n1 = __popc(p1);
+    if (b0 >= 0 && r0 == 0) hA[b0] = n0;             // one writer per bin and half
+    if (b1 >= 0 && r1 == 0) hB[b1] = n1;
+    __syncwarp();
+    const int other1 = (b0 >= 0) ? hB[b0] : 0;      // edges of my bin in the second half
+    __syncwarp();
+    int base = 0;
+    for (int f0 = 0; f0 < FP; f0 += 32) {
+        const int c0 = hA[f0 + lane], c1 = hB[f0 + lane], t = c0 + c1;
+        int incl = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const int excl = base + incl - t;
+        hA[f0 + lane] = excl;                        // where half-0 edges of this bin start
+        hB[f0 + lane] = excl + c0;                   // where half-1 edges of this bin start
+        base += __shfl_sync(FULL_MASK, incl, 31);
+    }
+    if (lane == 0) hA[FP] = base;
+    __syncwarp();
+    if (b0 >= 0) {
+        const int pos = hA[b0] + r0;
+        sOff[pos] = o0;
+        sCode[pos] = (b0 << 1) | ((r0 == n0 - 1 && other1 == 0) ? 1 : 0);
+    }
+    if (b1 >= 0) {
+        const int pos = hB[b1] + r1;
+        sOff[pos] = o1;
+        sCode[pos] = (b1 << 1) | ((r1 == n1 - 1) ? 1 : 0);
+    }
+    __syncwarp();
+}
+
+// ints of shared memory one warp needs for sort_tile_by_bin
+static __host__ __device__ inline int sort_smem_ints(int F) { int FP = ((F + 31) / 32) * 32; return (FP + 1 + 3) / 4 * 4 + FP + 64 + 64; }
+
 struct ConvPlan {
     int vec;          // 4 / 2 / 1, 0 = generic fallback
     int chunks;       // gridDim.y: channel chunks of 32*vec
@@ -122,7 +181,16 @@ static inline bool fits_32bit(int B, int N, int M, int C, int r)
 
 // rows are handed to CTAs in contiguous chunks so that the warps sharing an SM's L1 work on
 // neighbouring rows (the "first K by index" rule makes neighbouring rows share most neighbours)
-constexpr int ROWS_PER_CHUNK = 128;
+// Launch-shape tunables (defaults are what bench.py measures; the SPH3D_* environment variables exist
+// for the sweeps documented in DESIGN.md and are read once per call on the host).
+static inline int tune_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    int x = atoi(v);
+    return x > 0 ? x : dflt;
+}
+static inline int rows_per_chunk() { return tune_int("SPH3D_ROWS_PER_CHUNK", 128); }
 
 template <typename Kern>
 static cudaError_t set_smem(Kern k, size_t bytes)

@@ -29,7 +29,7 @@ int g_last_launch_count = 0;
 
 template <int VEC, int R>
 __global__ void __launch_bounds__(1024, 1)
-conv_fwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K,
+conv_fwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, int K,
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                 const int* __restrict__ bin_index, const float* __restrict__ input,
                 const float* __restrict__ filter, float* __restrict__ output)
@@ -49,11 +49,17 @@ conv_fwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K,
     const unsigned strideB = (unsigned)C * 4u;
     const size_t cloudB = (size_t)N * C * 4;
     const float* wlane = Wsh + S::offset(0, lane);
-    const unsigned nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    const unsigned nchunks = (rows + rpc - 1) / rpc;
+    // per-warp scratch of the bin sort, behind the filter
+    const int FP = ((F + 31) / 32) * 32;
+    int* hA = reinterpret_cast<int*>(Wsh + (size_t)F * S::FLOATS) + (size_t)warp * sort_smem_ints(F);
+    int* hB = hA + (FP + 1 + 3) / 4 * 4;
+    unsigned* sOff = reinterpret_cast<unsigned*>(hB + FP);
+    int* sCode = reinterpret_cast<int*>(sOff + 64);
 
     for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const unsigned rbeg = chunk * ROWS_PER_CHUNK;
-        const unsigned rend = min(rbeg + ROWS_PER_CHUNK, rows);
+        const unsigned rbeg = chunk * rpc;
+        const unsigned rend = min(rbeg + rpc, rows);
         unsigned row = rbeg + warp;
         if (row >= rend) continue;
         RowCursor cur;
@@ -73,34 +79,47 @@ conv_fwd_kernel(unsigned rows, int N, unsigned M, int F, int C, int K,
                 int b0 = -1, b1 = -1;
                 if (k0 < cnt) { o0 = (unsigned)__ldg(idxrow + k0) * strideB; b0 = __ldg(binrow + k0); }
                 if (k1 < cnt) { o1 = (unsigned)__ldg(idxrow + k1) * strideB; b1 = __ldg(binrow + k1); }
-                auto do_bin = [&](int f) {
-                    const unsigned m0 = __ballot_sync(FULL_MASK, b0 == f);
-                    const unsigned m1 = __ballot_sync(FULL_MASK, b1 == f);
-                    if (!(m0 | m1)) return;
-                    float s[VEC];
+                // group the tile's edges by bin (shared-memory counting sort), then one flat gather loop
+                sort_tile_by_bin(o0, b0, o1, b1, FP, lane, hA, hB, sOff, sCode);
+                const int nt = min(64, cnt - kt);
+                float s[VEC];
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) s[v] = 0.f;
-                    gather_sum_lean<VEC>(s, m0, o0, inb);
-                    gather_sum_lean<VEC>(s, m1, o1, inb);
-                    float w[E];
-                    S::load(w, wlane + f * S::FLOATS, 0);
-                    if constexpr (E % 2 == 0) {
+                for (int v = 0; v < VEC; v++) s[v] = 0.f;
+                auto consume = [&](const float (&v)[VEC], int code) {
+                    strip_add<VEC>(s, v);
+                    if (code & 1) {                               // last edge of its bin: apply the filter strip once
+                        float w[E];
+                        S::load(w, wlane + (code >> 1) * S::FLOATS, 0);
+                        if constexpr (E % 2 == 0) {
 #pragma unroll
-                        for (int e = 0; e < E; e += 2) {        // FFMA2: (acc[e],acc[e+1]) += (s,s') * (w[e],w[e+1])
-                            float2 a = __ffma2_rn(make_float2(s[e / R], s[(e + 1) / R]), make_float2(w[e], w[e + 1]),
-                                                  make_float2(acc[e], acc[e + 1]));
-                            acc[e] = a.x; acc[e + 1] = a.y;
+                            for (int e = 0; e < E; e += 2) {      // FFMA2: (acc[e],acc[e+1]) += (s,s') * (w[e],w[e+1])
+                                float2 a = __ffma2_rn(make_float2(s[e / R], s[(e + 1) / R]), make_float2(w[e], w[e + 1]),
+                                                      make_float2(acc[e], acc[e + 1]));
+                                acc[e] = a.x; acc[e + 1] = a.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < E; e++) acc[e] = fmaf(s[e / R], w[e], acc[e]);
                         }
-                    } else {
 #pragma unroll
-                        for (int e = 0; e < E; e++) acc[e] = fmaf(s[e / R], w[e], acc[e]);
+                        for (int v2 = 0; v2 < VEC; v2++) s[v2] = 0.f;
                     }
                 };
-                unsigned plo, phi;
-                present_bins(b0, b1, plo, phi);
-                while (plo) do_bin(pop_lowest(plo));
-                while (phi) do_bin(32 + pop_lowest(phi));
-                for (int f = 64; f < F; f++) do_bin(f);
+                int p = 0;
+                for (; p + 4 <= nt; p += 4) {                     // four independent gathers in flight
+                    const uint4 oo = *reinterpret_cast<const uint4*>(sOff + p);
+                    const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
+                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+                    ld_strip<VEC>(v0, inb, oo.x); ld_strip<VEC>(v1, inb, oo.y);
+                    ld_strip<VEC>(v2, inb, oo.z); ld_strip<VEC>(v3, inb, oo.w);
+                    consume(v0, cc.x); consume(v1, cc.y); consume(v2, cc.z); consume(v3, cc.w);
+                }
+                for (; p < nt; p++) {
+                    float v0[VEC];
+                    ld_strip<VEC>(v0, inb, sOff[p]);
+                    consume(v0, sCode[p]);
+                }
+                __syncwarp();                                     // sOff/sCode are rewritten by the next tile/row
             }
             if (active) {
                 const float inv = cnt > 0 ? 1.0f / (float)cnt : 0.f;
@@ -144,21 +163,25 @@ conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict
 static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
 {
     ConvPlan p{0, 0, 0, 0, 0, 0};
-    if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r)) return p;
+    if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 128) return p;
     int vec = pick_vec(C);
+    const size_t sort_bytes = (size_t)32 * sort_smem_ints(F) * sizeof(int);     // 32 warps
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
-    while (smem > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
-    if (smem > SMEM_CAP) return p;
+    while (smem + sort_bytes > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
+    if (smem + sort_bytes > SMEM_CAP) return p;
+    smem += sort_bytes;
     p.vec = vec; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
     const long long rows = (long long)B * M;
-    const long long nchunks = (rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+    const int rpc = rows_per_chunk();
+    const long long nchunks = (rows + rpc - 1) / rpc;
     long long want = sm_count();                                   // one persistent 32-warp CTA per SM ...
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;      // ... shared by the channel chunks
     if (want < 1) want = 1;
     p.grid_x = (int)(nchunks < want ? nchunks : want);
     // small problems: fewer warps per CTA so that more SMs get work
-    p.threads = 1024;
+    p.threads = tune_int("SPH3D_FWD_THREADS", 1024);
+    if (p.threads > 1024 || p.threads % 32) p.threads = 1024;
     while (p.threads > 128 && (long long)p.grid_x * p.chunks * (p.threads / 32) > rows && p.grid_x * p.chunks < sm_count())
         p.threads >>= 1;
     return p;
@@ -189,12 +212,13 @@ extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, 
     }
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * M);
+    const unsigned rpc = (unsigned)rows_per_chunk();
     cudaError_t e = cudaSuccess;
-#define LAUNCH_FWD(V, RR)                                                                            \
+#define LAUNCH_FWD(V, RR)                                                                           \
     do {                                                                                             \
         e = set_smem(conv_fwd_kernel<V, RR>, p.smem);                                                \
         if (e != cudaSuccess) return (int)e;                                                         \
-        conv_fwd_kernel<V, RR><<<grid, p.threads, p.smem, st>>>(rows, N, (unsigned)M, F, C, K,       \
+        conv_fwd_kernel<V, RR><<<grid, p.threads, p.smem, st>>>(rows, rpc, N, (unsigned)M, F, C, K,  \
                                                                 nn_index, nn_count, bin_index,       \
                                                                 input, filter, output);              \
     } while (0)
