@@ -43,6 +43,75 @@ __device__ __forceinline__ void warp_argmax(int bits, int key, int& wbits, int& 
     wkey = __reduce_min_sync(FULL_MASK, bits == wbits ? key : 0x7fffffff);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Single-CTA kernel (clouds of up to 1024*P points, P <= 10): the fastest path, because one round then
+// costs a bar.sync instead of a cluster barrier + DSMEM traffic.  Thread t owns points t, t+1024, ...
+// in registers (xyz + running min distance); the whole cloud additionally sits in shared memory so the
+// coordinates of the round's winner are three broadcast LDS away (no global load on the critical path,
+// and no per-thread "which of my points won" select chain).  Distance updates use Blackwell's packed
+// fp32x2 pipe (FADD2 / FMUL2 / FFMA2) on pairs of points -- two independent IEEE round-to-nearest
+// operations per instruction, so results are bit-identical to the scalar reference order (Q6/Q12).
+template <int P>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_single_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* __restrict__ out)
+{
+    extern __shared__ __align__(16) float fps_smem[];
+    float* sxyz = fps_smem;                                   // [N*3]
+    int* sbits = reinterpret_cast<int*>(fps_smem + ((N * 3 + 3) / 4) * 4);   // [2][32]
+    int* skey = sbits + 64;                                   // [2][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* pts = xyz + (size_t)cloud * N * 3;
+    for (int i = tid; i < N * 3; i += FPS_THREADS) sxyz[i] = __ldg(pts + i);
+    __syncthreads();
+
+    constexpr int P2 = (P + 1) / 2;                           // point pairs
+    float2 px[P2], py[P2], pz[P2], td[P2];
+#pragma unroll
+    for (int h = 0; h < P2; h++) {
+        float c[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            int k = (2 * h + u) * FPS_THREADS + tid;
+            bool ok = (2 * h + u < P) && (k < N);
+            c[u][0] = ok ? sxyz[3 * k] : 0.f; c[u][1] = ok ? sxyz[3 * k + 1] : 0.f; c[u][2] = ok ? sxyz[3 * k + 2] : 0.f;
+            c[u][3] = ok ? 1e38f : -1.f;                      // -1 never beats best = -1 (strict >)
+        }
+        px[h] = make_float2(c[0][0], c[1][0]); py[h] = make_float2(c[0][1], c[1][1]);
+        pz[h] = make_float2(c[0][2], c[1][2]); td[h] = make_float2(c[0][3], c[1][3]);
+    }
+    float x1 = sxyz[0], y1 = sxyz[1], z1 = sxyz[2];
+    if (tid == 0) out[(size_t)cloud * npoint] = 0;
+
+    for (int j = 1; j < npoint; j++) {
+        const int buf = (j & 1) * 32;
+        const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
+        float best = -1.f; int bp = 0;
+#pragma unroll
+        for (int h = 0; h < P2; h++) {
+            const float2 dx = __fadd2_rn(px[h], nx), dy = __fadd2_rn(py[h], ny), dz = __fadd2_rn(pz[h], nz);
+            float2 d = __fmul2_rn(dy, dy);                    // y product rounded alone (Q6) ...
+            d = __ffma2_rn(dx, dx, d);                        // ... x and z products fused
+            d = __ffma2_rn(dz, dz, d);
+            const float a = fminf(d.x, td[h].x), b = fminf(d.y, td[h].y);
+            td[h] = make_float2(a, b);
+            if (a > best) { best = a; bp = 2 * h; }           // ascending k inside the thread, strict '>'
+            if (2 * h + 1 < P) { if (b > best) { best = b; bp = 2 * h + 1; } }
+        }
+        const int bits = __float_as_int(best);
+        const int key = (tid << 21) | bp;                     // (k mod 1024, k / 1024): the reference's tie order
+        int wbits, wkey;
+        warp_argmax(bits, key, wbits, wkey);
+        if (lane == 0) { sbits[buf + warp] = wbits; skey[buf + warp] = wkey; }
+        __syncthreads();
+        int gb, gk;
+        warp_argmax(sbits[buf + lane], skey[buf + lane], gb, gk);
+        const int k = ((gk & 0x1fffff) << 10) | (gk >> 21);
+        x1 = sxyz[3 * k]; y1 = sxyz[3 * k + 1]; z1 = sxyz[3 * k + 2];
+        if (tid == 0) out[(size_t)cloud * npoint + j] = k;
+    }
+}
+
 template <int CS, int P>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* __restrict__ out)
@@ -169,6 +238,7 @@ struct FpsPlan { int cs, p; };
 
 static FpsPlan plan_fps(int n)
 {
+    if (n <= 10 * FPS_THREADS) return FpsPlan{1, (n + FPS_THREADS - 1) / FPS_THREADS};   // single-CTA kernel
     const int cs_opts[4] = {1, 2, 4, 8};
     for (int i = 0; i < 4; i++) {
         int cs = cs_opts[i];
@@ -194,6 +264,30 @@ static cudaError_t launch_fps(int B, int N, int npoint, const float* xyz, int* o
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CS, P>, B, N, npoint, xyz, out);
+}
+
+template <int P>
+static cudaError_t launch_fps_single(int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
+{
+    const size_t smem = (size_t)((N * 3 + 3) / 4) * 4 * sizeof(float) + 128 * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fps_single_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fps_single_kernel<P><<<B, FPS_THREADS, smem, st>>>(B, N, npoint, xyz, out);
+    return cudaPeekAtLastError();
+}
+
+static cudaError_t launch_fps_single_p(int p, int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
+{
+    switch (p) {
+        case 1: return launch_fps_single<1>(B, N, npoint, xyz, out, st);
+        case 2: return launch_fps_single<2>(B, N, npoint, xyz, out, st);
+        case 3: case 4: return launch_fps_single<4>(B, N, npoint, xyz, out, st);
+        case 5: case 6: return launch_fps_single<6>(B, N, npoint, xyz, out, st);
+        case 7: case 8: return launch_fps_single<8>(B, N, npoint, xyz, out, st);
+        default: return launch_fps_single<10>(B, N, npoint, xyz, out, st);
+    }
 }
 
 template <int CS>
@@ -240,7 +334,7 @@ extern "C" int sph3d_farthest_point_sample(int b, int n, int m, const float* inp
         int grid = b < sm_count() ? b : sm_count();
         fps_global_kernel<<<grid, FPS_THREADS, 0, st>>>(b, n, m, inp, (float*)temp, out);
         e = cudaPeekAtLastError();
-    } else if (p.cs == 1) e = launch_fps_p<1>(p.p, b, n, m, inp, out, st);
+    } else if (p.cs == 1) e = launch_fps_single_p(p.p, b, n, m, inp, out, st);
     else if (p.cs == 2) e = launch_fps_p<2>(p.p, b, n, m, inp, out, st);
     else if (p.cs == 4) e = launch_fps_p<4>(p.p, b, n, m, inp, out, st);
     else e = launch_fps_p<8>(p.p, b, n, m, inp, out, st);
