@@ -36,8 +36,11 @@ __device__ __forceinline__ void red_strip(char* __restrict__ base, unsigned off,
     VecIO<VEC>::red(reinterpret_cast<float*>(base + off), d);
 }
 
+// threads per CTA the register budget allows: 9 bins/warp -> <= 85 registers -> 24 warps; 17 -> 16 warps
+__host__ __device__ constexpr int bwd_max_threads(int vec, int r, int slots) { return (slots * vec * r <= 36) ? 768 : BWD_THREADS; }
+
 template <int VEC, int R, int SLOTS>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(bwd_max_threads(VEC, R, SLOTS), 1)
 conv_bwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, int K, int G,
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                 const int* __restrict__ bin_index, const float* __restrict__ input,
@@ -225,13 +228,15 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     {   // sweep knob: a larger group (fewer bins per warp) is always legal
         int g_env = tune_int("SPH3D_BWD_G", G);
         if ((g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) && g_env > G) G = g_env;
+        if (G * 9 >= F) slots = 9;                      // fewer bins per warp -> fewer registers -> more warps
     }
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
     if (smem > SMEM_CAP) return p;
     p.vec = vec; p.slots = slots; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
-    p.threads = tune_int("SPH3D_BWD_THREADS", BWD_THREADS);
-    if (p.threads > BWD_THREADS || p.threads % (32 * G)) p.threads = BWD_THREADS;
+    const int max_threads = bwd_max_threads(vec, r, slots) / (32 * G) * (32 * G);
+    p.threads = tune_int("SPH3D_BWD_THREADS", max_threads);
+    if (p.threads > max_threads || p.threads % (32 * G)) p.threads = max_threads;
     const long long rows = (long long)B * M;
     const int rpc = rows_per_chunk();
     const long long nchunks = (rows + rpc - 1) / rpc;
