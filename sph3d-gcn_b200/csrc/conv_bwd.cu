@@ -45,7 +45,7 @@ conv_bwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                 const int* __restrict__ bin_index, const float* __restrict__ input,
                 const float* __restrict__ filter, const float* __restrict__ grad_output,
-                float* __restrict__ grad_input, float* __restrict__ gw_partial)
+                float* __restrict__ grad_input, float* __restrict__ gw_partial, int cta_reduce)
 {
     constexpr int E = VEC * R;
     using S = SmemStrip<E>;
@@ -145,6 +145,32 @@ conv_bwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
                 }
             }
         }
+    }
+    if (cta_reduce) {
+        // sum the groups of this CTA in shared memory (fixed group order) and emit ONE partial per CTA:
+        // 8x fewer partial bytes for the second-stage reduction than one partial per group
+        float* gsm = smem + (size_t)F * S::FLOATS;                   // [ngroups][F][strip]
+        __syncthreads();
+        {
+            int f = wig;
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++, f += G)
+                if (f < F) S::store(gsm + ((size_t)group * F + f) * S::FLOATS, lane, acc[s]);
+        }
+        __syncthreads();
+        float* part = gw_partial + (size_t)blockIdx.x * F * C * R;
+        for (int t = threadIdx.x; t < F * S::FLOATS; t += blockDim.x) {
+            const int f = t / S::FLOATS, rem = t % S::FLOATS;
+            const int ln = rem / E, e = rem % E;
+            const int c = cbase + ln * VEC + e / R;
+            if (c < C) {
+                float sum = 0.f;
+                const int off = f * S::FLOATS + S::flat(ln, e);
+                for (int gq = 0; gq < ngroups; gq++) sum += gsm[(size_t)gq * F * S::FLOATS + off];
+                part[((size_t)f * C + c) * R + (e % R)] = sum;
+            }
+        }
+        return;
     }
     // partial [blockIdx.x][group][f][c][j]: each (f, c-chunk) is written by exactly one warp of the group
     float* part = gw_partial + ((size_t)blockIdx.x * ngroups + group) * F * C * R;
@@ -247,11 +273,18 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     while (p.threads > 32 * G && p.threads > 64 &&
            (long long)p.grid_x * p.chunks * (p.threads / (32 * G)) > rows && p.grid_x * p.chunks < sm_count())
         p.threads >>= 1;
+    {   // room to sum the CTA's groups in shared memory?  (filter + one filter-sized slab per group)
+        const size_t need = smem * (1 + (size_t)(p.threads / 32 / G));
+        if (need <= SMEM_CAP) { p.cta_reduce = 1; p.smem = need; }
+    }
     *G_out = G;
     return p;
 }
 
-static size_t bwd_partials(const ConvPlan& p, int G) { return (size_t)p.grid_x * (p.threads / 32 / G); }
+static size_t bwd_partials(const ConvPlan& p, int G)
+{
+    return p.cta_reduce ? (size_t)p.grid_x : (size_t)p.grid_x * (p.threads / 32 / G);
+}
 
 }  // namespace sph3d
 
@@ -307,7 +340,8 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
         conv_bwd_kernel<V, RR, SL><<<grid, p.threads, p.smem, st>>>(rows, rpc, N, (unsigned)M, F, C, K, \
                                                                     G, nn_index, nn_count,           \
                                                                     bin_index, input, filter,        \
-                                                                    grad_output, grad_input, part);  \
+                                                                    grad_output, grad_input, part,   \
+                                                                    p.cta_reduce);                   \
     } while (0)
 #define DISPATCH_SLOTS(V, RR)                                                                        \
     do {                                                                                             \

@@ -167,6 +167,7 @@ struct ConvPlan {
     int threads;      // CTA size
     int slots;        // backward: filter bins owned per warp
     size_t smem;      // dynamic shared memory bytes
+    int cta_reduce;   // backward: groups of a CTA are summed in shared memory before the partial is written
 };
 
 static inline int pick_vec(int C) { return (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1); }
