@@ -193,18 +193,27 @@ conv_bwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
     }
 }
 
+// second stage: out[t] = sum_p part[p][t] in a FIXED order (bit-reproducible).  A CTA owns 32 consecutive
+// elements; its 8 warps split the partials (warp w takes p = w, w+8, ...), then warp 0 adds the 8 sums.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(int P, size_t n, const float* __restrict__ part, float* __restrict__ out)
 {
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int p = 0;
-        for (; p + 3 < P; p += 4) {
-            s0 += part[(size_t)p * n + t]; s1 += part[(size_t)(p + 1) * n + t];
-            s2 += part[(size_t)(p + 2) * n + t]; s3 += part[(size_t)(p + 3) * n + t];
-        }
-        for (; p < P; p++) s0 += part[(size_t)p * n + t];
-        out[t] = (s0 + s1) + (s2 + s3);
+    __shared__ float sm[8][32];
+    const int tx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const size_t t = (size_t)blockIdx.x * 32 + tx;
+    float s0 = 0.f, s1 = 0.f;
+    if (t < n) {
+        int p = py;
+        for (; p + 8 < P; p += 16) { s0 += part[(size_t)p * n + t]; s1 += part[(size_t)(p + 8) * n + t]; }
+        if (p < P) s0 += part[(size_t)p * n + t];
+    }
+    sm[py][tx] = s0 + s1;
+    __syncthreads();
+    if (py == 0 && t < n) {
+        float s = sm[0][tx];
+#pragma unroll
+        for (int w = 1; w < 8; w++) s += sm[w][tx];
+        out[t] = s;
     }
 }
 
@@ -273,9 +282,11 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     while (p.threads > 32 * G && p.threads > 64 &&
            (long long)p.grid_x * p.chunks * (p.threads / (32 * G)) > rows && p.grid_x * p.chunks < sm_count())
         p.threads >>= 1;
-    {   // room to sum the CTA's groups in shared memory?  (filter + one filter-sized slab per group)
+    {   // Summing the CTA's groups in shared memory (one partial per CTA) is OFF by default: the 8 extra
+        // filter-sized slabs move the L1/shared carve-out from ~200 KB of L1 to ~76 KB and the gathers
+        // lose more (2.27 -> 2.42 ms at Cfg-T) than the smaller second-stage reduction saves.
         const size_t need = smem * (1 + (size_t)(p.threads / 32 / G));
-        if (need <= SMEM_CAP) { p.cta_reduce = 1; p.smem = need; }
+        if (need <= SMEM_CAP && tune_int("SPH3D_BWD_CTA_REDUCE", 2) == 1) { p.cta_reduce = 1; p.smem = need; }
     }
     *G_out = G;
     return p;
@@ -357,7 +368,7 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
 #undef DISPATCH_SLOTS
 #undef LAUNCH_BWD
     SPH3D_CHECK_LAUNCH();
-    reduce_partials_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((int)P, nW, part, grad_filter);
+    reduce_partials_kernel<<<(unsigned)((nW + 31) / 32), 256, 0, st>>>((int)P, nW, part, grad_filter);
     SPH3D_CHECK_LAUNCH();
     g_last_launch_count = 2;        // kernels only (the cudaMemsetAsync of grad_input is not counted)
     return 0;
