@@ -112,80 +112,99 @@ fps_single_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster kernel (clouds of 10 241 .. 81 920 points): CS CTAs of one thread-block cluster share a cloud,
+// thread t of CTA `rank` owns points (p*CS + rank)*1024 + t in registers; the CTA's points also sit in its
+// shared memory.  A round is two-level: (1) 32 warp records -> bar.sync -> warp 0 picks the CTA winner and
+// reads its coordinates from shared memory; (2) warp 0 pushes ONE 20-byte record per CTA into every
+// cluster CTA's shared memory (DSMEM), one cluster barrier, everybody reduces the CS records.
+// (Pushing all 32 warp records of every CTA through DSMEM instead costs 2.4 us/round; measured.)
+template <int CS>
+struct ClusterSlots {
+    int lbits[2][32], lkey[2][32];                      // local warp records
+    int cbits[2][CS], ckey[2][CS];                      // one record per cluster CTA (written remotely)
+    float cx[2][CS], cy[2][CS], cz[2][CS];
+};
+
 template <int CS, int P>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* __restrict__ out)
 {
-    __shared__ FpsSlots<CS> slots;
+    extern __shared__ __align__(16) float fps_smem[];
+    float* lxyz = fps_smem;                             // [P*1024*3] this CTA's points, local index p*1024 + t
+    __shared__ ClusterSlots<CS> slots;
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int rank = 0;
-    if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
+    const int rank = (int)cluster.block_rank();
     const int cloud = blockIdx.x / CS;
     const float* pts = xyz + (size_t)cloud * N * 3;
 
-    float px[P], py[P], pz[P], td[P];
+    constexpr int P2 = (P + 1) / 2;
+    float2 px[P2], py[P2], pz[P2], td[P2];
 #pragma unroll
-    for (int p = 0; p < P; p++) {
-        int k = (p * CS + rank) * FPS_THREADS + tid;
-        if (k < N) { px[p] = __ldg(pts + 3 * k); py[p] = __ldg(pts + 3 * k + 1); pz[p] = __ldg(pts + 3 * k + 2); td[p] = 1e38f; }
-        else { px[p] = py[p] = pz[p] = 0.f; td[p] = -1.f; }       // never beats best = -1
+    for (int h = 0; h < P2; h++) {
+        float c[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int p = 2 * h + u;
+            const int k = (p * CS + rank) * FPS_THREADS + tid;
+            const bool ok = (p < P) && (k < N);
+            c[u][0] = ok ? __ldg(pts + 3 * k) : 0.f; c[u][1] = ok ? __ldg(pts + 3 * k + 1) : 0.f;
+            c[u][2] = ok ? __ldg(pts + 3 * k + 2) : 0.f; c[u][3] = ok ? 1e38f : -1.f;
+            if (p < P) {
+                const int li = p * FPS_THREADS + tid;
+                lxyz[3 * li] = c[u][0]; lxyz[3 * li + 1] = c[u][1]; lxyz[3 * li + 2] = c[u][2];
+            }
+        }
+        px[h] = make_float2(c[0][0], c[1][0]); py[h] = make_float2(c[0][1], c[1][1]);
+        pz[h] = make_float2(c[0][2], c[1][2]); td[h] = make_float2(c[0][3], c[1][3]);
     }
     float x1 = __ldg(pts), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
     if (rank == 0 && tid == 0) out[(size_t)cloud * npoint] = 0;
+    cluster.sync();                                     // peers' shared memory exists before anyone writes to it
 
     for (int j = 1; j < npoint; j++) {
         const int buf = j & 1;
+        const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
         float best = -1.f; int bp = 0;
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            float d = sqdist_ref(__fsub_rn(px[p], x1), __fsub_rn(py[p], y1), __fsub_rn(pz[p], z1));
-            float d2 = fminf(d, td[p]);
-            td[p] = d2;
-            if (d2 > best) { best = d2; bp = p; }
+        for (int h = 0; h < P2; h++) {
+            const float2 dx = __fadd2_rn(px[h], nx), dy = __fadd2_rn(py[h], ny), dz = __fadd2_rn(pz[h], nz);
+            float2 d = __fmul2_rn(dy, dy);
+            d = __ffma2_rn(dx, dx, d);
+            d = __ffma2_rn(dz, dz, d);
+            const float a = fminf(d.x, td[h].x), b = fminf(d.y, td[h].y);
+            td[h] = make_float2(a, b);
+            if (a > best) { best = a; bp = 2 * h; }
+            if (2 * h + 1 < P) { if (b > best) { best = b; bp = 2 * h + 1; } }
         }
-        const int bits = __float_as_int(best);
-        const int key = (tid << 21) | (bp * CS + rank);
         int wbits, wkey;
-        warp_argmax(bits, key, wbits, wkey);
-        // winner lane publishes its coordinates to the warp
-        float wx = px[0], wy = py[0], wz = pz[0];
-#pragma unroll
-        for (int p = 1; p < P; p++) if (bp == p) { wx = px[p]; wy = py[p]; wz = pz[p]; }
-        const int src = __ffs(__ballot_sync(FULL_MASK, bits == wbits && key == wkey)) - 1;
-        wx = __shfl_sync(FULL_MASK, wx, src);
-        wy = __shfl_sync(FULL_MASK, wy, src);
-        wz = __shfl_sync(FULL_MASK, wz, src);
-        const int e = rank * 32 + warp;
-        if constexpr (CS == 1) {
-            if (lane == 0) {
-                slots.bits[buf][e] = wbits; slots.key[buf][e] = wkey;
-                slots.x[buf][e] = wx; slots.y[buf][e] = wy; slots.z[buf][e] = wz;
-            }
-            __syncthreads();
-        } else {
-            cg::cluster_group cluster = cg::this_cluster();
+        warp_argmax(__float_as_int(best), (tid << 21) | (bp * CS + rank), wbits, wkey);
+        if (lane == 0) { slots.lbits[buf][warp] = wbits; slots.lkey[buf][warp] = wkey; }
+        __syncthreads();
+        if (warp == 0) {
+            int gb, gk;
+            warp_argmax(slots.lbits[buf][lane], slots.lkey[buf][lane], gb, gk);
+            const int kk = ((gk & 0x1fffff) << 10) | (gk >> 21);            // global point id of the CTA winner
+            const int li = ((kk >> 10) / CS) * FPS_THREADS + (kk & (FPS_THREADS - 1));
+            const float wx = lxyz[3 * li], wy = lxyz[3 * li + 1], wz = lxyz[3 * li + 2];
             if (lane < CS) {
-                FpsSlots<CS>* rs = cluster.map_shared_rank(&slots, lane);
-                rs->bits[buf][e] = wbits; rs->key[buf][e] = wkey;
-                rs->x[buf][e] = wx; rs->y[buf][e] = wy; rs->z[buf][e] = wz;
+                ClusterSlots<CS>* rs = cluster.map_shared_rank(&slots, lane);
+                rs->cbits[buf][rank] = gb; rs->ckey[buf][rank] = gk;
+                rs->cx[buf][rank] = wx; rs->cy[buf][rank] = wy; rs->cz[buf][rank] = wz;
             }
-            cluster.sync();
         }
-        // every warp reduces the 32*CS records
-        int mb = slots.bits[buf][lane], mk = slots.key[buf][lane], me = lane;
+        cluster.sync();
+        int fb, fk;
+        warp_argmax(lane < CS ? slots.cbits[buf][lane] : (int)0x80000000, lane < CS ? slots.ckey[buf][lane] : 0x7fffffff, fb, fk);
+        int wl = 0;
 #pragma unroll
-        for (int c = 1; c < CS; c++) {
-            int ob = slots.bits[buf][c * 32 + lane], ok = slots.key[buf][c * 32 + lane];
-            if (ob > mb || (ob == mb && ok < mk)) { mb = ob; mk = ok; me = c * 32 + lane; }
-        }
-        int gb, gk;
-        warp_argmax(mb, mk, gb, gk);
-        const int wl = __ffs(__ballot_sync(FULL_MASK, mb == gb && mk == gk)) - 1;
-        const int we = __shfl_sync(FULL_MASK, me, wl);
-        x1 = slots.x[buf][we]; y1 = slots.y[buf][we]; z1 = slots.z[buf][we];
-        if (rank == 0 && tid == 0) out[(size_t)cloud * npoint + j] = ((gk & 0x1fffff) << 10) | (gk >> 21);
+        for (int c = 1; c < CS; c++) if (slots.cbits[buf][c] == fb && slots.ckey[buf][c] == fk) wl = c;
+        if (slots.cbits[buf][0] == fb && slots.ckey[buf][0] == fk) wl = 0;
+        x1 = slots.cx[buf][wl]; y1 = slots.cy[buf][wl]; z1 = slots.cz[buf][wl];
+        if (rank == 0 && tid == 0) out[(size_t)cloud * npoint + j] = ((fk & 0x1fffff) << 10) | (fk >> 21);
     }
-    if constexpr (CS > 1) cg::this_cluster().sync();       // no CTA may exit while peers still write its smem
+    cluster.sync();                                     // no CTA may exit while peers can still write its smem
 }
 
 // Any-N fallback: one CTA per cloud, running min distances in a global workspace.
@@ -256,7 +275,12 @@ static cudaError_t launch_fps(int B, int N, int npoint, const float* xyz, int* o
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * CS);
     cfg.blockDim = dim3(FPS_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)P * FPS_THREADS * 3 * sizeof(float);
+    if (cfg.dynamicSmemBytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<CS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)cfg.dynamicSmemBytes);
+        if (e != cudaSuccess) return e;
+    }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
