@@ -54,7 +54,7 @@ def test_cfgT_full_batch_adjoint_identity(pkg):
     sw = float((W.grad.double() * W.detach().double()).sum())
     assert abs(si - s) <= 1e-5 * abs(s) + 1e-2 and abs(sw - s) <= 1e-5 * abs(s) + 1e-2, (s, si, sw)
     # rows are convex-ish combinations: |out| <= max|x| * max|W| summed over nothing more than cnt terms / cnt
-    assert float(out.abs().max()) <= float(x.abs().max()) * float(W.abs().max()) * 1.0001
+    assert float(out.detach().abs().max()) <= float(x.detach().abs().max()) * float(W.detach().abs().max()) * 1.0001
 
 
 def test_fps_full_sizes_vs_oracle(pkg, oracle):

@@ -355,3 +355,51 @@ def test_layer_pipeline_matches_oracle(pkg, oracle):
     assert_close(A(net).reshape(-1, Cout), y.numpy(), 2e-5, "separable_conv3d (ELU before BN)")
     assert x_t.grad is not None and torch.isfinite(x_t.grad).all()
     assert vars_['conv1_1/depthwise_weights'].grad is not None
+
+
+# ------------------------------------------------------------------------- stream / graph semantics
+def test_ops_are_cuda_graph_capturable(pkg, oracle):
+    """include/sph3d_b200.h promises stream-ordered, allocation-free, sync-free entry points: capture the
+    whole layer slice (ball query, bins, FPS, conv fwd+bwd, max-pool) in a CUDA graph, replay it on new
+    inputs, and compare with the oracle."""
+    B, N, K, C, r, S = 2, 1024, 20, 16, 2, 128
+    L = pkg._lib.lib()
+    dev = torch.device(DEV)
+    xyz = torch.empty(B, N, 3, device=dev); x = torch.empty(B, N, C, device=dev)
+    W = T(features(131, 33, C, r) * 0.3); go = T(features(132, B, N, C * r))
+    idx = torch.empty(B, N, K, dtype=torch.int32, device=dev); cnt = torch.empty(B, N, dtype=torch.int32, device=dev)
+    dst = torch.empty(B, N, K, device=dev); filt = torch.empty_like(idx)
+    sel = torch.empty(B, S, dtype=torch.int32, device=dev)
+    out = torch.empty(B, N, C * r, device=dev); gi = torch.empty(B, N, C, device=dev); gf = torch.empty(33, C, r, device=dev)
+    ws_bytes = L.sph3d_depthwise_conv3d_grad_workspace_bytes(B, N, N, 33, C, r, K)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=dev)
+    p = lambda t: t.data_ptr()
+
+    def enqueue(st):
+        rc = L.sph3d_build_sphere_neighbor(B, N, N, K, 0.15, p(xyz), p(xyz), p(idx), p(cnt), p(dst), st)
+        rc |= L.sph3d_spherical_kernel(B, N, N, K, 8, 2, 2, 0.15, p(xyz), p(xyz), p(idx), p(cnt), p(dst), p(filt), st)
+        rc |= L.sph3d_farthest_point_sample(B, N, S, p(xyz), None, 0, p(sel), st)
+        rc |= L.sph3d_depthwise_conv3d(B, N, N, 33, C, r, K, p(idx), p(cnt), p(filt), p(x), p(W), p(out), st)
+        rc |= L.sph3d_depthwise_conv3d_grad(B, N, N, 33, C, r, K, p(idx), p(cnt), p(filt), p(x), p(W), p(go), p(gi), p(gf),
+                                            p(ws), ws_bytes, st)
+        assert rc == 0
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        enqueue(side.cuda_stream)                       # warm-up outside capture (sets the smem attributes once)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        enqueue(torch.cuda.current_stream().cuda_stream)
+    for seed in (141, 142):
+        xyz_np, x_np = make_cloud(seed, B, N, "cube"), features(seed + 10, B, N, C)
+        xyz.copy_(T(xyz_np)); x.copy_(T(x_np))
+        graph.replay()
+        torch.cuda.synchronize()
+        oi, oc, od = oracle.build_sphere_neighbor(xyz_np, xyz_np, 0.15, None, K)
+        of = oracle.spherical_kernel(xyz_np, xyz_np, oi, oc, od, 0.15, [8, 2, 2])
+        assert_equal(A(idx), oi); assert_equal(A(cnt), oc); assert_equal(A(filt), of)
+        assert_equal(A(sel), oracle.farthest_point_sample(S, xyz_np))
+        assert_close(A(out), oracle.depthwise_conv3d(x_np, A(W), oi, oc, of, 1), 1e-5)
+        ti, tf = oracle.depthwise_conv3d_grad(x_np, A(W), A(go), oi, oc, of)
+        assert_close(A(gi), ti, 1e-5); assert_close(A(gf), tf, 1e-5)
