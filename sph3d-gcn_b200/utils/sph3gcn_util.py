@@ -150,14 +150,41 @@ else:
         return nn_idx, nn_cnt, nn_dst
 
 
+    _SIDE_STREAMS = {}
+
+    def _side_stream(device):
+        key = (device.type, device.index)
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        return _SIDE_STREAMS[key]
+
+
     def build_graph(xyz, radius, nn_uplimit, num_sample, sample_method=None):
+        # FPS depends only on xyz and occupies one SM per cloud for `num_sample` sequential rounds, so it is
+        # enqueued FIRST on a side stream and overlaps the ball query (which fills the other SMs); the main
+        # stream waits for it before `indices` is built.  Same results, shorter critical path.
+        fps_event = None
+        if num_sample is not None and sample_method == 'FPS' and xyz.is_cuda:
+            cur = torch.cuda.current_stream(xyz.device)
+            side = _side_stream(xyz.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sample_index = farthest_point_sample(num_sample, xyz)
+                fps_event = torch.cuda.Event()
+                fps_event.record(side)
+            xyz.record_stream(side)
+
         intra_idx, intra_cnt, intra_dst = neighbor_fn(xyz, xyz, radius=radius, nnsample=nn_uplimit)
 
         if num_sample is not None:
             if sample_method == 'random':
                 sample_index = random_sample(num_sample, xyz)
             elif sample_method == 'FPS':
-                sample_index = farthest_point_sample(num_sample, xyz)
+                if fps_event is not None:
+                    cur.wait_event(fps_event)
+                    sample_index.record_stream(cur)
+                else:
+                    sample_index = farthest_point_sample(num_sample, xyz)
             elif sample_method == 'IDS':
                 prob = intra_dst.sum(dim=-1) / intra_cnt.to(torch.float32)
                 sample_index = inverse_density_sample(num_sample, prob)
@@ -226,13 +253,25 @@ else:
             depthwise_kernel = _variable_with_weight_decay('depthwise_weights', shape=depthwise_kernel_shape,
                                                            use_xavier=use_xavier, stddev=stddev,
                                                            with_decay=weight_decay, device=inputs.device)
-            outputs = tf_conv3d.depthwise_conv3d(inputs, depthwise_kernel, nn_index, nn_count, filt_index)
+            # Channel counts that are not a multiple of 4 (ModelNet's 32+3, 64+3, 128+3 after the raw-xyz concat)
+            # would take the scalar-strip kernels; zero-padding the channel axis of the input and of both weight
+            # tensors is exact (zeros contribute nothing, gradients flow through the pads) and keeps the op on
+            # the 16-byte-vector kernels.  The VARIABLES keep the reference's shapes.
+            pad = (-num_in_channels) % 4
+            if pad:
+                outputs = tf_conv3d.depthwise_conv3d(F.pad(inputs, (0, pad)), F.pad(depthwise_kernel, (0, 0, 0, pad)),
+                                                     nn_index, nn_count, filt_index)
+            else:
+                outputs = tf_conv3d.depthwise_conv3d(inputs, depthwise_kernel, nn_index, nn_count, filt_index)
 
             batch_size = outputs.shape[0]
-            num_in_channels = outputs.shape[-1]
+            num_in_channels = num_in_channels * depth_multiplier
             kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
                                                  use_xavier=use_xavier, stddev=stddev,
                                                  with_decay=weight_decay, device=inputs.device)
+            if pad:
+                kernel = F.pad(kernel, (0, 0, 0, pad * depth_multiplier))
+                num_in_channels += pad * depth_multiplier
             outputs = torch.matmul(outputs.reshape(-1, num_in_channels), kernel)
             outputs = outputs.reshape(batch_size, -1, num_out_channels)
             return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)

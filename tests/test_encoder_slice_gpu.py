@@ -14,6 +14,35 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "profiles"))
 
 
+def test_separable_conv_odd_channels_matches_oracle(pkg, oracle):
+    """C=35 (32 + raw xyz): the layer zero-pads channels to 36 to stay on the vector kernels; results and
+    gradients must equal the un-padded oracle, and the variables keep the reference's shapes."""
+    from common import assert_close, features, make_cloud, saturating_radius
+    u = pkg.sph3gcn_util
+    u.reset_variables()
+    B, N, K, C, r, Cout = 2, 700, 32, 35, 2, 24
+    xyz = make_cloud(151, B, N, "cube")
+    rad = saturating_radius(N, K)
+    idx, cnt, dst = oracle.build_sphere_neighbor(xyz, xyz, rad, None, K)
+    filt = oracle.spherical_kernel(xyz, xyz, idx, cnt, dst, rad, [8, 2, 2])
+    x = features(152, B, N, C)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")
+    xt = t(x).requires_grad_(True)
+    y = u.separable_conv3d(xt, Cout, 33, r, 'odd', t(idx), t(cnt), t(filt), activation_fn=None)
+    v = u.named_variables()
+    Wd, Wp = v['odd/depthwise_weights'], v['odd/weights']
+    assert tuple(Wd.shape) == (33, C, r) and tuple(Wp.shape) == (C * r, Cout)
+    dw = oracle.depthwise_conv3d(x, Wd.detach().cpu().numpy(), idx, cnt, filt, 1)
+    want = dw.reshape(-1, C * r).astype(np.float64) @ Wp.detach().cpu().numpy().astype(np.float64)
+    assert_close(y.detach().cpu().numpy().reshape(-1, Cout), want, 2e-5, "separable_conv3d C=35")
+    go = features(153, B, N, Cout)
+    y.backward(t(go))
+    g_dw = (go.reshape(-1, Cout).astype(np.float64) @ Wp.detach().cpu().numpy().astype(np.float64).T).reshape(B, N, C * r).astype(np.float32)
+    gi, gf = oracle.depthwise_conv3d_grad(x, Wd.detach().cpu().numpy(), g_dw, idx, cnt, filt)
+    assert_close(xt.grad.cpu().numpy(), gi, 2e-5, "grad_input through the padded layer")
+    assert_close(Wd.grad.cpu().numpy(), gf, 2e-5, "grad depthwise_weights through the padded layer")
+
+
 def test_modelnet_encoder_slice_runs_and_trains(pkg):
     import bench_encoder as be
     rec = be.run(B=2, N=2048, steps=1, warmup=1)
