@@ -64,32 +64,6 @@ __device__ __forceinline__ int pop_highest(unsigned& m)
     return b;
 }
 
-// Sum the feature strips of the edges selected by the warp-uniform mask m.  Bit k <-> the byte offset
-// held by lane k in `myoff`.  Up to four independent gathers in flight; every branch is warp-uniform;
-// no padding work.
-template <int VEC>
-__device__ __forceinline__ void gather_sum_lean(float (&s)[VEC], unsigned m, unsigned myoff,
-                                                const char* __restrict__ inb)
-{
-    while (m) {
-        float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
-        ld_strip<VEC>(v0, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
-        if (m) {
-            ld_strip<VEC>(v1, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
-            if (m) {
-                ld_strip<VEC>(v2, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
-                if (m) {
-                    ld_strip<VEC>(v3, inb, __shfl_sync(FULL_MASK, myoff, pop_highest(m)));
-                    strip_add<VEC>(s, v3);
-                }
-                strip_add<VEC>(s, v2);
-            }
-            strip_add<VEC>(s, v1);
-        }
-        strip_add<VEC>(s, v0);
-    }
-}
-
 // Incremental (cloud, point) bookkeeping for a warp that visits rows row0, row0+step, ... of a
 // contiguous chunk: avoids a division per row.
 struct RowCursor {

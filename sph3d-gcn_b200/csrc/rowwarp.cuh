@@ -115,40 +115,4 @@ struct SmemStrip {
     }
 };
 
-// Sum the feature strips of the neighbours whose bit is set in m (bit k <-> the neighbour id held
-// by lane k in `myidx`).  m is warp-uniform, so all branching below is uniform; up to four
-// independent gathers are in flight per call round.
-template <int VEC>
-__device__ __forceinline__ void gather_sum(float (&s)[VEC], unsigned m, int myidx,
-                                           const float* __restrict__ inb, int C, bool active)
-{
-    while (m) {
-        int l0 = pop_lowest(m);
-        bool p1 = m != 0; int l1 = p1 ? pop_lowest(m) : l0;
-        bool p2 = m != 0; int l2 = p2 ? pop_lowest(m) : l0;
-        bool p3 = m != 0; int l3 = p3 ? pop_lowest(m) : l0;
-        int n0 = __shfl_sync(FULL_MASK, myidx, l0);
-        int n1 = __shfl_sync(FULL_MASK, myidx, l1);
-        int n2 = __shfl_sync(FULL_MASK, myidx, l2);
-        int n3 = __shfl_sync(FULL_MASK, myidx, l3);
-        float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
-        VecIO<VEC>::ld(v0, inb + (size_t)n0 * C, active);
-        VecIO<VEC>::ld(v1, inb + (size_t)n1 * C, active && p1);
-        VecIO<VEC>::ld(v2, inb + (size_t)n2 * C, active && p2);
-        VecIO<VEC>::ld(v3, inb + (size_t)n3 * C, active && p3);
-#pragma unroll
-        for (int v = 0; v < VEC; v++) s[v] += (v0[v] + v1[v]) + (v2[v] + v3[v]);
-    }
-}
-
-// bitmask (bins 0..63) of the bins present among the warp's (b0,b1) values; -1 = no edge
-__device__ __forceinline__ void present_bins(int b0, int b1, unsigned& lo, unsigned& hi)
-{
-    unsigned mlo = 0, mhi = 0;
-    if (b0 >= 0 && b0 < 32) mlo |= 1u << b0; else if (b0 >= 32 && b0 < 64) mhi |= 1u << (b0 - 32);
-    if (b1 >= 0 && b1 < 32) mlo |= 1u << b1; else if (b1 >= 32 && b1 < 64) mhi |= 1u << (b1 - 32);
-    lo = __reduce_or_sync(FULL_MASK, mlo);
-    hi = __reduce_or_sync(FULL_MASK, mhi);
-}
-
 }  // namespace sph3d
