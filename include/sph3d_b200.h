@@ -35,10 +35,15 @@ int sph3d_last_launch_count(void);
 
 /* ---- a1: buildSphereNeighborLauncher, tf_nnquery_gpu.cu:115-121 (kernel :15-65) --------------
  * Ball query with the reference's growing-radius chain semantics: bit-exact
- * nn_index / nn_count / nn_dist.  radius > 0, K > 0. */
+ * nn_index / nn_count / nn_dist.  radius > 0, K > 0.
+ * workspace (optional): sph3d_build_sphere_neighbor_workspace_bytes(...) bytes of device scratch for a
+ * uniform cell grid over the database clouds; with it, queries whose radius spans <= 2 cells are answered
+ * from the cell stencil instead of a full scan (same results).  Pass NULL/0 to always scan. */
+size_t sph3d_build_sphere_neighbor_workspace_bytes(int B, int N, int M, int K);
 int sph3d_build_sphere_neighbor(int B, int N, int M, int K, float radius,
                                 const float* database, const float* query,
-                                int* nn_index, int* nn_count, float* nn_dist, void* stream);
+                                int* nn_index, int* nn_count, float* nn_dist,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a2: buildCubeNeighborLauncher, tf_nnquery_gpu.cu:123-127 (kernel :72-113) ---------------
  * nn_index is (B,M,K,2): (point id, grid bin) interleaved; nn_count may be 0. */

@@ -22,7 +22,8 @@ _P = c_void_p
 SIGNATURES = {
     "sph3d_abi_version": (c_int, []),
     "sph3d_last_launch_count": (c_int, []),
-    "sph3d_build_sphere_neighbor": (c_int, [c_int] * 4 + [c_float] + [_P] * 6),
+    "sph3d_build_sphere_neighbor_workspace_bytes": (c_size_t, [c_int] * 4),
+    "sph3d_build_sphere_neighbor": (c_int, [c_int] * 4 + [c_float] + [_P] * 6 + [c_size_t, _P]),
     "sph3d_build_cube_neighbor": (c_int, [c_int] * 5 + [c_float] + [_P] * 5),
     "sph3d_spherical_kernel": (c_int, [c_int] * 7 + [c_float] + [_P] * 7),
     "sph3d_depthwise_conv3d": (c_int, [c_int] * 7 + [_P] * 7),

@@ -42,10 +42,13 @@ def build_sphere_neighbor(database, query, radius=0.1, dilation_rate=None, nnsam
     nn_index = torch.empty((B, M, K), dtype=torch.int32, device=dev)
     nn_count = torch.empty((B, M), dtype=torch.int32, device=dev)
     nn_dist = torch.empty((B, M, K), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.sph3d_build_sphere_neighbor_workspace_bytes(B, N, M, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     with torch.cuda.device(dev):
-        rc = _lib.lib().sph3d_build_sphere_neighbor(B, N, M, K, float(radius), _lib.ptr(database), _lib.ptr(query),
-                                                    _lib.ptr(nn_index), _lib.ptr(nn_count), _lib.ptr(nn_dist),
-                                                    _lib.stream_ptr())
+        rc = L.sph3d_build_sphere_neighbor(B, N, M, K, float(radius), _lib.ptr(database), _lib.ptr(query),
+                                           _lib.ptr(nn_index), _lib.ptr(nn_count), _lib.ptr(nn_dist),
+                                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
     _lib.check(rc, "build_sphere_neighbor")
     return nn_index, nn_count, nn_dist
 

@@ -373,10 +373,12 @@ def test_ops_are_cuda_graph_capturable(pkg, oracle):
     out = torch.empty(B, N, C * r, device=dev); gi = torch.empty(B, N, C, device=dev); gf = torch.empty(33, C, r, device=dev)
     ws_bytes = L.sph3d_depthwise_conv3d_grad_workspace_bytes(B, N, N, 33, C, r, K)
     ws = torch.empty(max(ws_bytes // 4, 1), device=dev)
+    nb = L.sph3d_build_sphere_neighbor_workspace_bytes(B, N, N, K)
+    nws = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
     p = lambda t: t.data_ptr()
 
     def enqueue(st):
-        rc = L.sph3d_build_sphere_neighbor(B, N, N, K, 0.15, p(xyz), p(xyz), p(idx), p(cnt), p(dst), st)
+        rc = L.sph3d_build_sphere_neighbor(B, N, N, K, 0.15, p(xyz), p(xyz), p(idx), p(cnt), p(dst), p(nws), nb, st)
         rc |= L.sph3d_spherical_kernel(B, N, N, K, 8, 2, 2, 0.15, p(xyz), p(xyz), p(idx), p(cnt), p(dst), p(filt), st)
         rc |= L.sph3d_farthest_point_sample(B, N, S, p(xyz), None, 0, p(sel), st)
         rc |= L.sph3d_depthwise_conv3d(B, N, N, 33, C, r, K, p(idx), p(cnt), p(filt), p(x), p(W), p(out), st)
