@@ -7,18 +7,13 @@ from .tf_nnquery import _xyz
 
 @torch.no_grad()
 def spherical_kernel(database, query, nn_index, nn_count, nn_dist, radius, kernel=[8, 2, 3]):
-    '''
-    Input:
-        database: (batch, npoint, 3+) float32 array, database points (x,y,z,...)
-        query:    (batch, mpoint, 3+) float32 array, query points (x,y,z,...)
-        nn_index: (batch, mpoint, nnsample) int32 array, neighbor indices
-        nn_count: (batch, mpoint) int32 array, number of neighbors
-        nn_dist:  (batch, mpoint, nnsample) float32, sqrt distance array
-        radius:   float32, range search radius
-        kernel:   list of 3 int32, spherical kernel size
-    Output:
-        filt_index: (batch, mpoint, nnsample) int32 array, filter bin indices
-    '''
+    """Spherical-kernel bin of every edge of a ball-query graph.
+
+    kernel = [n azimuth, p elevation, q radial] divisions; returns filt_index (B,M,K) int32 in [0, n*p*q]:
+    0 for the (near-)coincident "self" neighbour, otherwise 1 + radial*p*n + elevation*n + azimuth, computed
+    with the reference's mixed fp32/fp64 arithmetic on the sqrt-distances `nn_dist` and the nominal `radius`.
+    Padding slots (k >= nn_count) are 0.
+    """
     n, p, q = [int(v) for v in kernel]
     database = _xyz(database, "database")
     query = _xyz(query, "query")

@@ -14,18 +14,13 @@ def _xyz(t, name):
 
 @torch.no_grad()
 def build_sphere_neighbor(database, query, radius=0.1, dilation_rate=None, nnsample=100):
-    '''
-    Input:
-        database: (batch, npoint, 3+x) float32 array, database points
-        query:    (batch, mpoint, 3) float32 array, query points
-        radius:   float32, range search radius
-        dilation_rate: float32, dilation rate of range search
-        nnsample: int32, maximum number of neighbors to be sampled
-    Output:
-        nn_index: (batch, mpoint, nnsample) int32 array, neighbor indices
-        nn_count: (batch, mpoint) int32 array, number of neighbors
-        nn_dist:  (batch, mpoint, nnsample) float32, sqrt distance array
-    '''
+    """Ball query with the reference's semantics.
+
+    database (B,N,>=3) and query (B,M,>=3) float32 CUDA tensors (only xyz is used); the effective radius is
+    radius * dilation_rate when a dilation rate is given; at most `nnsample` neighbours per query.
+    Returns nn_index (B,M,K) int32 -- the first K in-range database ids in ascending order, zero padded --,
+    nn_count (B,M) int32 in [1,K] and nn_dist (B,M,K) float32 = sqrt of the Euclidean distance, zero padded.
+    """
     database = _xyz(database, "database")
     query = _xyz(query, "query")
     if dilation_rate is not None:
