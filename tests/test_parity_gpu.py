@@ -157,6 +157,9 @@ CONV_CASES = [
     ("c32_r3_generic", 2, 400, 24, 32, 3, (8, 2, 2)),
     ("k156_tiles", 2, 300, 156, 64, 2, (8, 2, 1)),
     ("f121_bins_gt_64", 1, 900, 64, 32, 1, (12, 2, 5)),
+    ("f193_generic_kernels", 1, 500, 32, 8, 1, (16, 4, 3)),
+    ("c1_r1_single_channel", 2, 300, 16, 1, 1, (8, 2, 2)),
+    ("c512_r2_four_chunks", 1, 200, 32, 512, 2, (8, 2, 2)),
 ]
 
 
