@@ -80,18 +80,72 @@ def encoder(points, is_training, config):
     return torch.cat(global_feat, dim=2).reshape(points.shape[0], -1)
 
 
-def run(B, N, steps, warmup=2, seed=7):
+class S3disConfig:                         # s3dis_seg/s3dis_config.py of the reference (scaled with num_input)
+    def __init__(self, num_input):
+        self.num_input, self.num_cls, self.mlp = num_input, 13, 64
+        self.num_sample = [num_input // 4, num_input * 3 // 32, num_input * 3 // 64, num_input // 64]   # 2048,768,384,128 @8192
+        self.radius = [0.1, 0.2, 0.4, 0.8]
+        self.nn_uplimit = [64, 64, 64, 64]
+        self.channels = [[128, 128], [256, 256], [256, 256], [512, 512]]
+        self.multiplier = [[2, 2], [2, 2], [2, 2], [2, 2]]
+        self.weight_decay = None
+        self.kernel, self.binSize = [8, 2, 2], 33
+        self.pool_method, self.unpool_method, self.sample = 'max', 'mean', 'FPS'
+        self.with_bn, self.with_bias = True, False
+
+
+def s3dis_model(points, is_training, config):
+    """SPH3D_s3dis.get_model (models/SPH3D_s3dis.py:35-111): encoder + decoder with skip concats -> per-point logits.
+    (The model's config-list `.reverse()` calls are done on copies.)"""
+    xyz = points[:, :, 0:3]
+    net = s3g_util.pointwise_conv3d(points, config.mlp, 'mlp1', weight_decay=config.weight_decay, with_bn=config.with_bn,
+                                    with_bias=config.with_bias, is_training=is_training)
+    xyz_layers, encoder_feats = [xyz], []
+    for l in range(len(config.radius)):
+        intra_idx, intra_cnt, intra_dst, indices = s3g_util.build_graph(xyz, config.radius[l], config.nn_uplimit[l],
+                                                                        config.num_sample[l], sample_method=config.sample)
+        filt_idx = s3g_util.spherical_kernel(xyz, xyz, intra_idx, intra_cnt, intra_dst, config.radius[l], kernel=config.kernel)
+        net = _separable_conv3d_block(net, config.channels[l], config.binSize, intra_idx, intra_cnt, filt_idx,
+                                      'conv' + str(l + 1), config.multiplier[l], weight_decay=config.weight_decay,
+                                      with_bn=config.with_bn, with_bias=config.with_bias, is_training=is_training)
+        encoder_feats.append(net)
+        if config.num_sample[l] > 1:
+            xyz = s3g_util.gather_nd(xyz, indices)
+            xyz_layers.append(xyz)
+            inter_idx = s3g_util.gather_nd(intra_idx, indices)
+            inter_cnt = s3g_util.gather_nd(intra_cnt, indices)
+            net = s3g_util.pool3d(net, inter_idx, inter_cnt, method=config.pool_method, scope='pool' + str(l + 1))
+    radius, uplimit = config.radius[::-1], config.nn_uplimit[::-1]
+    channels, multiplier = config.channels[::-1], config.multiplier[::-1]
+    xyz_layers, encoder_feats = xyz_layers[::-1], encoder_feats[::-1]
+    for l in range(len(radius)):
+        xyz, xyz_unpool = xyz_layers[l], xyz_layers[l + 1]
+        intra_idx, intra_cnt, intra_dst, inter_idx, inter_cnt, inter_dst = s3g_util.build_graph_deconv(
+            xyz, xyz_unpool, radius[l], uplimit[l])
+        filt_idx = s3g_util.spherical_kernel(xyz, xyz, intra_idx, intra_cnt, intra_dst, radius[l], kernel=config.kernel)
+        net = _separable_conv3d_block(net, channels[l], config.binSize, intra_idx, intra_cnt, filt_idx,
+                                      'deconv' + str(l + 1), multiplier[l], weight_decay=config.weight_decay,
+                                      with_bn=config.with_bn, with_bias=config.with_bias, is_training=is_training)
+        net = s3g_util.unpool3d(net, inter_idx, inter_cnt, inter_dst, method=config.unpool_method, scope='unpool' + str(l + 1))
+        net = torch.cat((net, encoder_feats[l]), dim=2)
+    return s3g_util.pointwise_conv3d(net, config.num_cls, scope='logits', with_bn=False, with_bias=config.with_bias,
+                                     activation_fn=None, is_training=is_training)
+
+
+def run(B, N, steps, warmup=2, seed=7, model="modelnet"):
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(seed)
     pts = torch.rand(B, N, 3, generator=g).to(dev)            # unit cube, like a normalised ModelNet cloud
-    cfg = ModelNetConfig(N)
+    cfg = ModelNetConfig(N) if model == "modelnet" else S3disConfig(N)
     s3g_util.reset_variables()
+    if model != "modelnet":                                    # xyz + 3 extra input features (rgb in the reference)
+        pts = torch.cat([pts, torch.rand(B, N, 3, generator=g).to(dev)], dim=2)
 
     def step():
         s3g_util.clear_collections()
         for p in s3g_util.trainable_variables():
             p.grad = None
-        feat = encoder(pts, True, cfg)
+        feat = encoder(pts, True, cfg) if model == "modelnet" else s3dis_model(pts, True, cfg).reshape(B, -1)
         loss = feat.square().mean() + sum(s3g_util.get_collection('losses'))
         loss.backward()
         return feat, loss
@@ -108,7 +162,8 @@ def run(B, N, steps, warmup=2, seed=7):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     grads = [p.grad for p in s3g_util.trainable_variables()]
-    return {"workload": "modelnet 3-level encoder fwd+bwd (configs[1])", "B": B, "N": N, "levels": cfg.num_sample,
+    what = "modelnet 3-level encoder fwd+bwd (configs[1])" if model == "modelnet" else "s3dis encoder+decoder fwd+bwd (configs[3])"
+    return {"workload": what, "B": B, "N": N, "levels": cfg.num_sample,
             "ms_per_step": ms, "points_per_s": B * N / (ms * 1e-3), "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
             "feature_dim": int(feat.shape[1]), "loss": float(loss), "n_params": len(grads),
             "all_grads_finite": bool(all(gr is not None and torch.isfinite(gr).all() for gr in grads))}
@@ -119,8 +174,9 @@ if __name__ == "__main__":
     ap.add_argument("--B", type=int, default=32)
     ap.add_argument("--N", type=int, default=10000)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--model", default="modelnet", choices=["modelnet", "s3dis"])
     a = ap.parse_args()
-    rec = run(a.B, a.N, a.steps)
+    rec = run(a.B, a.N, a.steps, model=a.model)
     print(json.dumps(rec))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "bench_encoder.json"), "w"), indent=1)
+    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "bench_%s.json" % ("encoder" if a.model == "modelnet" else "s3dis")), "w"), indent=1)

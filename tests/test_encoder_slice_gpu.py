@@ -43,6 +43,23 @@ def test_separable_conv_odd_channels_matches_oracle(pkg, oracle):
     assert_close(Wd.grad.cpu().numpy(), gf, 2e-5, "grad depthwise_weights through the padded layer")
 
 
+def test_s3dis_encoder_decoder_slice_runs_and_trains(pkg):
+    """segmentation family (models/SPH3D_s3dis.py:35-111): build_graph_deconv, inter-graph ball queries from the fine
+    to the coarse cloud (retries), mean unpooling and skip concats, forward + backward."""
+    import bench_encoder as be
+    B, N = 2, 1024
+    rec = be.run(B=B, N=N, steps=1, warmup=1, model="s3dis")
+    assert rec["levels"] == [256, 96, 48, 16]
+    assert rec["all_grads_finite"] and np.isfinite(rec["loss"])
+    assert rec["feature_dim"] == N * 13                                         # per-point logits
+    names = set(pkg.sph3gcn_util.named_variables())
+    for want in ("conv4_2/depthwise_weights", "deconv1_1/depthwise_weights", "deconv4_2/weights", "logits/weights"):
+        assert want in names, want
+    v = pkg.sph3gcn_util.named_variables()
+    assert tuple(v["deconv2_1/depthwise_weights"].shape) == (33, 512 + 512, 2)      # unpooled 512 (+) skip 512
+    assert all(float(p.grad.abs().sum()) > 0 for n, p in v.items() if n.endswith("depthwise_weights"))
+
+
 def test_modelnet_encoder_slice_runs_and_trains(pkg):
     import bench_encoder as be
     rec = be.run(B=2, N=2048, steps=1, warmup=1)
