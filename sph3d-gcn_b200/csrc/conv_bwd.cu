@@ -248,7 +248,14 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     ConvPlan p{0, 0, 0, 0, 0, 0};
     *G_out = 0;
     if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 136) return p;
-    int vec = pick_vec(C), slots = 0, G = 0;
+    int vec = pick_vec_full_warp(C), slots = 0, G = 0;
+    {   // sweep knob: force a strip width (must divide C)
+        int v_env = tune_int("SPH3D_BWD_VEC", vec);
+        if ((v_env == 1 || v_env == 2 || v_env == 4) && C % v_env == 0) vec = v_env;
+    }
+    // narrow strips (vec <= 2: C <= 64) keep few accumulators per bin: 9 bins per warp (4 warps per row) then fit in
+    // <= 36 registers and 24 warps per SM, which measured faster than 17 bins per warp (0.38 vs 0.48 ms, C=64, r=2)
+    if (vec <= 2 && 9 * vec * r <= 36 && 4 * 9 >= F && tune_int("SPH3D_BWD_G", 4) == 4) { G = 4; slots = 9; }
     for (; vec >= 1 && !G; vec = (vec > 1 ? vec >> 1 : 0)) {
         const int slot_opts[2] = {17, 9};
         for (int i = 0; i < 2 && !G; i++) {

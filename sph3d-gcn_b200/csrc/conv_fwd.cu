@@ -164,7 +164,11 @@ static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
 {
     ConvPlan p{0, 0, 0, 0, 0, 0};
     if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 128) return p;
-    int vec = pick_vec(C);
+    int vec = pick_vec_full_warp(C);
+    {   // sweep knob: force a strip width (must divide C)
+        int v_env = tune_int("SPH3D_FWD_VEC", vec);
+        if ((v_env == 1 || v_env == 2 || v_env == 4) && C % v_env == 0) vec = v_env;
+    }
     const size_t sort_bytes = (size_t)32 * sort_smem_ints(F) * sizeof(int);     // 32 warps
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
     while (smem + sort_bytes > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
