@@ -159,7 +159,15 @@ max_pool_grad_kernel(int B, int N, int M, int C, const int* __restrict__ max_ind
     }
 }
 
-static inline int pick_vec(int C) { return (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1); }
+// narrowest legal strip whose single chunk covers C, so that small channel counts still use all 32 lanes
+// (same rule as the convolution, conv_common.cuh::pick_vec_full_warp)
+static inline int pick_vec(int C)
+{
+    const int widest = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
+    for (int v = 1; v <= widest; v <<= 1)
+        if (C % v == 0 && C <= 32 * v) return v;
+    return widest;
+}
 
 static dim3 row_grid(int B, int rows_per_cloud, int C, int vec)
 {
