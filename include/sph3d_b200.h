@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SPH3D_B200_ABI_VERSION 1
+#define SPH3D_B200_ABI_VERSION 2
 int sph3d_abi_version(void);
 
 /* Number of KERNELS (memsets excluded) the most recent entry-point call enqueued (bench.py gpu_launches). */
@@ -65,14 +65,34 @@ int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, int K,
                            const float* input, const float* filter, float* output, void* stream);
 
 /* ---- a5: depthwiseConv3dGradLauncher, tf_conv3d_gpu.cu:115-140 (kernels :32-101) -------------
- * workspace: sph3d_depthwise_conv3d_grad_workspace_bytes(...) bytes of device scratch (per-CTA
- * filter-gradient partials, reduced in a fixed order => grad_filter is deterministic). */
+ * workspace: sph3d_depthwise_conv3d_grad_workspace_bytes(...) bytes of device scratch (transposed graph,
+ * scaled grad_output, per-CTA filter-gradient partials reduced in a fixed order => grad_filter is
+ * deterministic run to run). */
 size_t sph3d_depthwise_conv3d_grad_workspace_bytes(int B, int N, int M, int F, int C, int r, int K);
 int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, int r, int K,
                                 const int* nn_index, const int* nn_count, const int* bin_index,
                                 const float* input, const float* filter, const float* grad_output,
                                 float* grad_input, float* grad_filter,
                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a5, split form: the same launcher with its graph-only work hoisted out -------------------------------
+ * sph3d_depthwise_conv3d_grad first transposes the graph (per input point n: the (output point, bin) pairs that
+ * reference it, grouped by bin) and then runs one gather pass.  The transposed graph depends only on
+ * (nn_index, nn_count, bin_index, F); a caller that applies several convolutions over one graph (the reference's
+ * models run two per level: sph3gcn_util.py:88-161 called twice per level in models/SPH3D_*.py) or
+ * steps a static graph builds it once with sph3d_conv_transpose and passes it to ..._grad_planned.
+ * sph3d_conv_transpose_bytes returns 0 when the planned form does not apply (F > 72, M >= 2^24);
+ * sph3d_depthwise_conv3d_grad_planned_workspace_bytes returns 0 when (C, r) is not covered (r > 2). */
+size_t sph3d_conv_transpose_bytes(int B, int N, int M, int F, int K);
+int sph3d_conv_transpose(int B, int N, int M, int F, int K,
+                         const int* nn_index, const int* nn_count, const int* bin_index,
+                         void* plan, size_t plan_bytes, void* stream);
+size_t sph3d_depthwise_conv3d_grad_planned_workspace_bytes(int B, int N, int M, int F, int C, int r, int K);
+int sph3d_depthwise_conv3d_grad_planned(int B, int N, int M, int F, int C, int r, int K,
+                                        const int* nn_count, const void* plan, size_t plan_bytes,
+                                        const float* input, const float* filter, const float* grad_output,
+                                        float* grad_input, float* grad_filter,
+                                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a6: farthestPointSampleLauncher, tf_sample_gpu.cu:77-80 (kernel :7-73) ------------------
  * temp: the reference's (32,n) scratch (tf_sample.cpp:50) becomes a caller-owned workspace of

@@ -29,6 +29,10 @@ SIGNATURES = {
     "sph3d_depthwise_conv3d": (c_int, [c_int] * 7 + [_P] * 7),
     "sph3d_depthwise_conv3d_grad_workspace_bytes": (c_size_t, [c_int] * 7),
     "sph3d_depthwise_conv3d_grad": (c_int, [c_int] * 7 + [_P] * 9 + [c_size_t, _P]),
+    "sph3d_conv_transpose_bytes": (c_size_t, [c_int] * 5),
+    "sph3d_conv_transpose": (c_int, [c_int] * 5 + [_P] * 4 + [c_size_t, _P]),
+    "sph3d_depthwise_conv3d_grad_planned_workspace_bytes": (c_size_t, [c_int] * 7),
+    "sph3d_depthwise_conv3d_grad_planned": (c_int, [c_int] * 7 + [_P, _P, c_size_t] + [_P] * 6 + [c_size_t, _P]),
     "sph3d_farthest_point_sample_workspace_bytes": (c_size_t, [c_int] * 3),
     "sph3d_farthest_point_sample": (c_int, [c_int] * 3 + [_P, _P, c_size_t, _P, _P]),
     "sph3d_max_pool3d": (c_int, [c_int] * 5 + [_P] * 6),
@@ -65,7 +69,7 @@ def lib():
         fn = getattr(handle, name)      # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if handle.sph3d_abi_version() != 1:
+    if handle.sph3d_abi_version() != 2:
         raise ImportError("sph3d-gcn_b200: ABI version mismatch in %s" % path)
     _LIB = handle
     return _LIB

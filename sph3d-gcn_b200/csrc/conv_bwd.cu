@@ -304,6 +304,13 @@ static size_t bwd_partials(const ConvPlan& p, int G)
     return p.cta_reduce ? (size_t)p.grid_x : (size_t)p.grid_x * (p.threads / 32 / G);
 }
 
+int launch_reduce_partials(int P, size_t n, const float* part, float* out, cudaStream_t st)
+{
+    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(P, n, part, out);
+    SPH3D_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace sph3d
 
 using namespace sph3d;
@@ -311,6 +318,7 @@ using namespace sph3d;
 extern "C" size_t sph3d_depthwise_conv3d_grad_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
 {
     if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0) return 0;
+    if (bwd_transposed_supported(B, N, M, F, C, r, K)) return bwd_transposed_workspace_bytes(B, N, M, F, C, r, K);
     int G = 0;
     ConvPlan p = plan_bwd(B, N, M, F, C, r, &G);
     if (p.vec == 0) return 0;
@@ -328,6 +336,9 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
         !bin_index || !input || !filter || !grad_output || !grad_input || !grad_filter)
         return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
+    if (bwd_transposed_supported(B, N, M, F, C, r, K))
+        return bwd_transposed_run(B, N, M, F, C, r, K, nn_index, nn_count, bin_index, input, filter, grad_output,
+                                  grad_input, grad_filter, workspace, workspace_bytes, st);
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
     if (e != cudaSuccess) return (int)e;
     int G = 0;

@@ -1,0 +1,612 @@
+// conv_bwd_t.cu -- depthwise spherical graph convolution, backward, "transposed" form, sm_100a.
+//
+// Same contract as conv_bwd.cu (replaces depthwiseConv3dGradLauncher,
+// /root/reference/tf_ops/convolution/tf_conv3d_gpu.cu:115-140, kernels :32-101), different algorithm.
+//
+// The reference (and conv_bwd.cu) walk the graph row by row of the OUTPUT points m and scatter into
+// grad_input with one float reduction per edge and channel; on B200 those E*C reductions are the floor
+// of that form (L2 reduction throughput).  Here the graph is first TRANSPOSED: for every
+// INPUT point n the list of (output point m, bin f) pairs that reference it, grouped by bin.  With
+//      T[n,f,:] = sum_{m : (m -> n) in bin f} gO[b,m,:] / cnt[b,m]              (one gather per edge)
+// both gradients are plain gathers and register sums -- no per-edge atomics at all:
+//      grad_input [b,n,c]   = sum_f sum_j W[f,c,j] * T[n,f,c*r+j]
+//      grad_filter[f,c,j]   = sum_{b,n} in[b,n,c] * T[n,f,c*r+j]
+// so ONE pass over the edges (E strips of C*r floats gathered from gO) replaces one gather pass plus one
+// reduction pass.
+//
+// Pipeline of one call (all on the caller's stream, caller-owned workspace):
+//   1. transpose_count : seg[(b,n), f'] += 1 per edge (integer RED), f' = (f % G)*SLOTS + f / G
+//   2. exclusive scan of seg (two small kernels), 3. transpose_fill: entries[pos] = (m << 8) | (f / G)
+//      with pos from an integer atomic cursor; afterwards seg[s] is the END of segment s
+//   4. (optional, default on) per-segment insertion sort of the entries by m => run-to-run deterministic
+//   5. scale_rows: gs[b,m,:] = gO[b,m,:] / cnt[b,m] into a (B, M+1, C*r) buffer whose row M is zero
+//      (the landing row of the padding edges that round every tile up to a multiple of four)
+//   6. conv_bwd_t_kernel: a group of G warps shares an input point; warp w of the group owns the bins
+//      f = w, w+G, ... (SLOTS = 9 of them), i.e. ONE contiguous, bin-sorted sub-list of the point's
+//      entries.  Flat 4-deep gather loop over the sub-list (LDG.128 + FADD2); at the end of each bin
+//      segment: grad_input strip += W[f]*T (filter strip from shared memory, FFMA2) and the warp's REGISTER
+//      accumulator of that bin += in[n]*T (warp-uniform switch => static register indexing, no atomics, no
+//      shared-memory accumulation).  The G partial grad_input strips of a point meet in global memory with
+//      G vector reductions per point (E/K*G instead of E).
+//   7. reduce_partials_kernel (conv_bwd.cu) sums the per-group filter partials in a fixed order.
+// Steps 1-4 depend only on the graph: sph3d_conv_transpose() exposes them so that a caller who reuses a
+// graph (two convolutions per level, every training step of a static graph) builds the plan once.
+//
+// Channels are handled in FLAT output-channel space i = c*r + j (Co = C*r): lane l owns VEC consecutive
+// flat channels, so the kernel is the r=1 kernel plus an expansion of in[n,c] to flat channels and a
+// pairwise sum when grad_input is written (r = 2).
+#include "conv_common.cuh"
+#include "../../include/sph3d_b200.h"
+
+namespace sph3d {
+
+constexpr int T_SLOTS = 9;
+constexpr int SCAN_TILE = 4096;          // ints per CTA in the scan kernels (256 threads x 16)
+
+// ------------------------------------------------------------------------------------------- plan
+struct TGeom {
+    int G, FP;                  // warps per point, G*T_SLOTS segments per point
+    size_t nseg, nseg_pad;      // B*N*FP, rounded up to SCAN_TILE
+    int scan_blocks;
+    size_t seg_off, sums_off, ent_off, total;   // byte offsets inside the plan
+    bool ok;
+};
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static TGeom t_geom(int B, int N, int M, int F, int K)
+{
+    TGeom g{};
+    g.ok = false;
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || K <= 0) return g;
+    int G = (F + T_SLOTS - 1) / T_SLOTS;
+    if (G == 5) G = 6;
+    if (G == 7) G = 8;
+    if (G > 8) return g;                                          // F > 72: conv_bwd.cu handles it
+    if ((long long)M >= (1LL << 24)) return g;                    // m is packed into 24 bits
+    if ((long long)B * M * K >= (1LL << 31) || (long long)B * N >= (1LL << 31)) return g;
+    g.G = G; g.FP = G * T_SLOTS;
+    g.nseg = (size_t)B * N * g.FP;
+    g.nseg_pad = (g.nseg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+    if (g.nseg_pad / SCAN_TILE > 65536) return g;
+    g.scan_blocks = (int)(g.nseg_pad / SCAN_TILE);
+    g.seg_off = 0;
+    g.sums_off = align256(g.nseg_pad * sizeof(int));
+    g.ent_off = g.sums_off + align256((size_t)g.scan_blocks * sizeof(int));
+    g.total = g.ent_off + align256((size_t)B * M * K * sizeof(int));
+    g.ok = true;
+    return g;
+}
+
+// ------------------------------------------------------------------------------ transpose kernels
+// one thread per edge slot (b,m,k); edges beyond nn_count and malformed ids are skipped
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G, int FP,
+                       const int* __restrict__ nn_index, const int* __restrict__ nn_count,
+                       const int* __restrict__ bin_index, int* __restrict__ seg, unsigned* __restrict__ entries)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = t / (unsigned)K;
+        const int k = (int)(t - row * (unsigned)K);
+        if (k >= __ldg(nn_count + row)) continue;
+        const int n = __ldg(nn_index + t), f = __ldg(bin_index + t);
+        if ((unsigned)n >= N || (unsigned)f >= (unsigned)F) continue;
+        const unsigned b = (unsigned)(row / M);
+        const unsigned m = (unsigned)(row - (size_t)b * M);
+        const size_t s = ((size_t)b * N + n) * FP + (f % G) * T_SLOTS + f / G;
+        if constexpr (FILL) {
+            const int pos = atomicAdd(seg + s, 1);
+            entries[pos] = (m << 8) | (unsigned)(f / G);
+        } else {
+            atomicAdd(seg + s, 1);                                  // result unused: RED.ADD
+        }
+    }
+}
+
+__device__ __forceinline__ int block_sum_256(int v, int* sm)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tot += sm[i];
+    __syncthreads();
+    return tot;
+}
+
+__global__ void __launch_bounds__(256)
+scan_reduce_kernel(const int4* __restrict__ seg4, int* __restrict__ sums)
+{
+    __shared__ int sm[8];
+    const int4* p = seg4 + (size_t)blockIdx.x * (SCAN_TILE / 4);
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int4 v = p[j * 256 + threadIdx.x];
+        s += v.x + v.y + v.z + v.w;
+    }
+    const int tot = block_sum_256(s, sm);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+// in-place exclusive scan of the CTA's 4096 counters, offset by the sum of all earlier CTAs
+__global__ void __launch_bounds__(256)
+scan_apply_kernel(int4* __restrict__ seg4, const int* __restrict__ sums)
+{
+    __shared__ int sm[8];
+    __shared__ int wtot[8];
+    int pre = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) pre += sums[i];
+    const int base = block_sum_256(pre, sm);
+    int4* p = seg4 + (size_t)blockIdx.x * (SCAN_TILE / 4) + threadIdx.x * 4;     // 16 consecutive ints per thread
+    int4 v[4];
+    int tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[j] = p[j]; tsum += v[j].x + v[j].y + v[j].z + v[j].w; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    int run = base + incl - tsum;
+    for (int i = 0; i < w; i++) run += wtot[i];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int4 o;
+        o.x = run; run += v[j].x;
+        o.y = run; run += v[j].y;
+        o.z = run; run += v[j].z;
+        o.w = run; run += v[j].w;
+        p[j] = o;
+    }
+}
+
+// canonical order inside every segment (ascending m): makes the float sums independent of the order in which the
+// fill kernel's atomic cursor handed out positions.  Segments are short (mean E / (#non-empty segments) ~ 4).
+__global__ void __launch_bounds__(256)
+sort_segments_kernel(size_t nseg, const int* __restrict__ seg, unsigned* __restrict__ entries)
+{
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (size_t)gridDim.x * blockDim.x) {
+        const int end = seg[s];
+        const int beg = s ? seg[s - 1] : 0;
+        for (int i = beg + 1; i < end; i++) {
+            const unsigned x = entries[i];
+            int j = i;
+            while (j > beg) {
+                const unsigned y = entries[j - 1];
+                if (y <= x) break;
+                entries[j] = y;
+                j--;
+            }
+            entries[j] = x;
+        }
+    }
+}
+
+// gs[b, m, :] = gO[b, m, :] / cnt[b, m]   (m < M);   gs[b, M, :] = 0      -- gs is (B, M+1, Co)
+template <int V>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(size_t total /* B*(M+1)*Co/V */, unsigned M, unsigned CoV, int K, const int* __restrict__ nn_count,
+                  const float* __restrict__ go, float* __restrict__ gs)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t rowp = t / CoV;
+        const unsigned i = (unsigned)(t - rowp * CoV);
+        const unsigned b = (unsigned)(rowp / (M + 1));
+        const unsigned m = (unsigned)(rowp - (size_t)b * (M + 1));
+        float v[V];
+#pragma unroll
+        for (int u = 0; u < V; u++) v[u] = 0.f;
+        if (m < M) {
+            const size_t row = (size_t)b * M + m;
+            const int cnt = min(__ldg(nn_count + row), K);
+            if (cnt > 0) {
+                const float inv = 1.0f / (float)cnt;
+                VecIO<V>::ld(v, go + (row * CoV + i) * V, true);
+#pragma unroll
+                for (int u = 0; u < V; u++) v[u] *= inv;
+            }
+        }
+        VecIO<V>::st(gs + t * V, v);
+    }
+}
+
+// -------------------------------------------------------------------------------------- main kernel
+template <int VEC>
+__device__ __forceinline__ void strip_fma(float (&a)[VEC], const float (&x)[VEC], const float (&y)[VEC])
+{
+    if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int e = 0; e < VEC; e += 2) {
+            const float2 t = __ffma2_rn(make_float2(x[e], x[e + 1]), make_float2(y[e], y[e + 1]), make_float2(a[e], a[e + 1]));
+            a[e] = t.x; a[e + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < VEC; e++) a[e] = fmaf(x[e], y[e], a[e]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void ld_strip_smem(float (&v)[VEC], const float* p)
+{
+    if constexpr (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = *p;
+    }
+}
+
+template <int VEC, int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp /* M+1 */, int F, int C, int G,
+                  const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
+                  const float* __restrict__ input, const float* __restrict__ filter,
+                  float* __restrict__ grad_input, float* __restrict__ gw_partial)
+{
+    static_assert(VEC % R == 0, "a lane's flat strip must cover whole input channels");
+    constexpr int VI = VEC / R;                          // input channels per lane
+    constexpr int SLOTS = T_SLOTS;
+    const int Co = C * R;
+    extern __shared__ __align__(16) float smem[];
+    float* Wsh = smem;                                   // [F][32*VEC] flat-channel filter strips of this chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = THREADS / 32;
+    const int wig = warp % G, group = warp / G, ngroups = nwarps / G;
+    const int cbase = blockIdx.y * 32 * VEC;             // first flat channel of this chunk
+    for (int t = threadIdx.x; t < F * 32 * VEC; t += THREADS) {
+        const int f = t / (32 * VEC), ch = cbase + t % (32 * VEC);
+        Wsh[t] = (ch < Co) ? __ldg(filter + (size_t)f * Co + ch) : 0.f;
+    }
+    unsigned* sOff = reinterpret_cast<unsigned*>(Wsh + (size_t)F * 32 * VEC) + warp * 128;
+    int* sCode = reinterpret_cast<int*>(sOff + 64);
+    __syncthreads();
+
+    const int i0 = cbase + lane * VEC;                   // my first flat channel
+    const bool active = i0 < Co;
+    const int i0ld = active ? i0 : 0;                    // idle lanes load a valid strip, never store
+    const int cin0 = i0ld / R;                           // my first input channel
+    const unsigned gsStrideB = (unsigned)Co * 4u;
+    const unsigned zoff = (Mp - 1u) * gsStrideB;         // the zero row of every cloud
+    const size_t gcloudB = (size_t)Mp * Co * 4;
+    const float* wlane = Wsh + lane * VEC;
+    const int FP = G * SLOTS;
+
+    float acc[SLOTS][VEC];
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[s][e] = 0.f;
+
+    const unsigned nchunks = (rows + rpc - 1) / rpc;
+    for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const unsigned rbeg = chunk * rpc;
+        const unsigned rend = min(rbeg + rpc, rows);
+        unsigned row = rbeg + group;
+        if (row >= rend) continue;
+        RowCursor cur;
+        cur.init(row, N);
+        for (; row < rend; row += ngroups, cur.advance(ngroups, N)) {
+            // my sub-list: segments [sb, sb+SLOTS) of this point; seg[s] = end of segment s
+            const size_t sb = (size_t)row * FP + wig * SLOTS;
+            int bv = 0;
+            if (lane == 0 && sb > 0) bv = __ldg(seg + sb - 1);
+            if (lane == 1) bv = __ldg(seg + sb + SLOTS - 1);
+            const int beg = __shfl_sync(FULL_MASK, bv, 0), end = __shfl_sync(FULL_MASK, bv, 1);
+            if (end <= beg) continue;
+
+            float inx[VEC];                               // in[b,n,c] expanded to my flat channels
+            {
+                float t[VI];
+                VecIO<VI>::ld(t, input + (size_t)row * C + cin0, true);
+#pragma unroll
+                for (int e = 0; e < VEC; e++) inx[e] = t[e / R];
+            }
+            float gi[VEC], T[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) { gi[e] = 0.f; T[e] = 0.f; }
+            const char* gb = reinterpret_cast<const char*>(gs) + cur.b * gcloudB + (size_t)i0ld * 4;
+
+            auto consume = [&](const float (&v)[VEC], int code) {
+                strip_add<VEC>(T, v);
+                if (code & 1) {                            // last edge of its bin segment (warp-uniform)
+                    const int s = code >> 1;
+                    float w[VEC];
+                    ld_strip_smem<VEC>(w, wlane + (s * G + wig) * 32 * VEC);
+                    strip_fma<VEC>(gi, w, T);
+                    switch (s) {                           // static register indexing of the owned bin
+                        case 0: strip_fma<VEC>(acc[0], inx, T); break;
+                        case 1: strip_fma<VEC>(acc[1], inx, T); break;
+                        case 2: strip_fma<VEC>(acc[2], inx, T); break;
+                        case 3: strip_fma<VEC>(acc[3], inx, T); break;
+                        case 4: strip_fma<VEC>(acc[4], inx, T); break;
+                        case 5: strip_fma<VEC>(acc[5], inx, T); break;
+                        case 6: strip_fma<VEC>(acc[6], inx, T); break;
+                        case 7: strip_fma<VEC>(acc[7], inx, T); break;
+                        default: strip_fma<VEC>(acc[8], inx, T); break;
+                    }
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) T[e] = 0.f;
+                }
+            };
+
+            for (int kt = beg; kt < end; kt += 64) {
+                const int nt = min(64, end - kt);
+                const int nt4 = (nt + 3) & ~3;
+                const int p0 = lane, p1 = 32 + lane;
+                unsigned e0 = 0, e1 = 0;
+                if (p0 < nt) e0 = __ldg(entries + kt + p0);
+                if (p1 < nt) e1 = __ldg(entries + kt + p1);
+                const int s0 = (int)(e0 & 255u), s1 = (int)(e1 & 255u);
+                int nx0 = __shfl_down_sync(FULL_MASK, s0, 1);
+                const int nx1 = __shfl_down_sync(FULL_MASK, s1, 1);
+                const int first1 = __shfl_sync(FULL_MASK, s1, 0);
+                if (lane == 31) nx0 = first1;
+                if (p0 < nt) {
+                    sOff[p0] = (e0 >> 8) * gsStrideB;
+                    sCode[p0] = (s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0);
+                } else if (p0 < nt4) {
+                    sOff[p0] = zoff; sCode[p0] = 0;
+                }
+                if (p1 < nt) {
+                    sOff[p1] = (e1 >> 8) * gsStrideB;
+                    sCode[p1] = (s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0);
+                } else if (p1 < nt4) {
+                    sOff[p1] = zoff; sCode[p1] = 0;
+                }
+                __syncwarp();
+                for (int p = 0; p < nt4; p += 4) {                 // four independent gathers in flight
+                    const uint4 oo = *reinterpret_cast<const uint4*>(sOff + p);
+                    const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
+                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+                    ld_strip<VEC>(v0, gb, oo.x); ld_strip<VEC>(v1, gb, oo.y);
+                    ld_strip<VEC>(v2, gb, oo.z); ld_strip<VEC>(v3, gb, oo.w);
+                    consume(v0, cc.x); consume(v1, cc.y); consume(v2, cc.z); consume(v3, cc.w);
+                }
+                __syncwarp();                                      // sOff/sCode are rewritten by the next tile/row
+            }
+            if (active) {
+                float o[VI];
+#pragma unroll
+                for (int v = 0; v < VI; v++) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int j = 0; j < R; j++) t += gi[v * R + j];
+                    o[v] = t;
+                }
+                VecIO<VI>::red(grad_input + (size_t)row * C + cin0, o);
+            }
+        }
+    }
+    // partial [blockIdx.x][group][f][flat channel]: every (f, channel) is written by exactly one warp of the group
+    if (active) {
+        float* part = gw_partial + ((size_t)blockIdx.x * ngroups + group) * F * Co;
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) {
+            const int f = s * G + wig;
+            if (f < F) VecIO<VEC>::st(part + (size_t)f * Co + i0, acc[s]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host helpers
+struct TPlanMain {
+    int vec, chunks, grid_x, threads, ngroups;
+    size_t smem;
+    unsigned rpc;
+};
+
+static bool t_plan_main(int B, int N, int M, int F, int C, int r, const TGeom& g, TPlanMain* out)
+{
+    if (!g.ok || (r != 1 && r != 2)) return false;
+    const long long Co = (long long)C * r;
+    if ((long long)(M + 1) * Co * 4 >= (1LL << 32)) return false;       // 32-bit byte offsets inside a cloud of gs
+    int vec = pick_vec_full_warp((int)Co);
+    if (vec % r != 0) vec = r;                                            // a lane's strip covers whole input channels (Co % r == 0)
+    TPlanMain p{};
+    p.vec = vec;
+    p.chunks = (int)((Co + 32 * vec - 1) / (32 * vec));
+    p.threads = 768;
+    if ((p.threads / 32) % g.G) return false;
+    p.ngroups = p.threads / 32 / g.G;
+    p.smem = (size_t)F * 32 * vec * sizeof(float) + (size_t)(p.threads / 32) * 128 * sizeof(int);
+    if (p.smem > SMEM_CAP) return false;
+    const long long rows = (long long)B * N;
+    p.rpc = (unsigned)tune_int("SPH3D_BWDT_ROWS_PER_CHUNK", 64);
+    const long long nchunks = (rows + p.rpc - 1) / p.rpc;
+    long long want = sm_count();
+    if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
+    if (want < 1) want = 1;
+    p.grid_x = (int)(nchunks < want ? nchunks : want);
+    *out = p;
+    return true;
+}
+
+static inline unsigned grid_for(size_t work, int threads, int per_sm)
+{
+    size_t want = (work + threads - 1) / threads, cap = (size_t)sm_count() * per_sm;
+    if (want < 1) want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const int* nn_index, const int* nn_count,
+                        const int* bin_index, char* plan, cudaStream_t st, int* launches)
+{
+    int* seg = reinterpret_cast<int*>(plan + g.seg_off);
+    int* sums = reinterpret_cast<int*>(plan + g.sums_off);
+    unsigned* ent = reinterpret_cast<unsigned*>(plan + g.ent_off);
+    cudaError_t e = cudaMemsetAsync(seg, 0, g.nseg_pad * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t slots = (size_t)B * M * K;
+    const unsigned ge = grid_for(slots, 256, 16);
+    transpose_edges_kernel<false><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.FP, nn_index, nn_count,
+                                                     bin_index, seg, ent);
+    SPH3D_CHECK_LAUNCH();
+    scan_reduce_kernel<<<g.scan_blocks, 256, 0, st>>>(reinterpret_cast<const int4*>(seg), sums);
+    SPH3D_CHECK_LAUNCH();
+    scan_apply_kernel<<<g.scan_blocks, 256, 0, st>>>(reinterpret_cast<int4*>(seg), sums);
+    SPH3D_CHECK_LAUNCH();
+    transpose_edges_kernel<true><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.FP, nn_index, nn_count,
+                                                    bin_index, seg, ent);
+    SPH3D_CHECK_LAUNCH();
+    *launches += 4;
+    if (tune_int("SPH3D_BWDT_SORT", 1) == 1) {
+        sort_segments_kernel<<<grid_for(g.nseg, 256, 16), 256, 0, st>>>(g.nseg, seg, ent);
+        SPH3D_CHECK_LAUNCH();
+        *launches += 1;
+    }
+    return 0;
+}
+
+// workspace of the gradient call proper (scaled grad_output + filter partials), after an optional plan
+struct TWork { size_t gs_off, part_off, total; size_t P; };
+
+static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
+{
+    TWork w{};
+    const size_t Co = (size_t)C * r;
+    w.gs_off = 0;
+    w.part_off = align256((size_t)B * (M + 1) * Co * sizeof(float));
+    w.P = (size_t)p.grid_x * p.ngroups;
+    w.total = w.part_off + align256(w.P * F * Co * sizeof(float));
+    return w;
+}
+
+static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGeom& g, const TPlanMain& p, const char* plan,
+                      const int* nn_count, const float* input, const float* filter, const float* grad_output,
+                      float* grad_input, float* grad_filter, char* work, cudaStream_t st, int* launches)
+{
+    const TWork w = t_work(B, M, F, C, r, p);
+    const size_t Co = (size_t)C * r;
+    float* gs = reinterpret_cast<float*>(work + w.gs_off);
+    float* part = reinterpret_cast<float*>(work + w.part_off);
+    const int* seg = reinterpret_cast<const int*>(plan + g.seg_off);
+    const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
+    cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
+    if (e != cudaSuccess) return (int)e;
+    {
+        const int V = (Co % 4 == 0) ? 4 : ((Co % 2 == 0) ? 2 : 1);
+        const size_t total = (size_t)B * (M + 1) * Co / V;
+        const unsigned gr = grid_for(total, 256, 16);
+        if (V == 4) scale_rows_kernel<4><<<gr, 256, 0, st>>>(total, (unsigned)M, (unsigned)(Co / 4), K, nn_count, grad_output, gs);
+        else if (V == 2) scale_rows_kernel<2><<<gr, 256, 0, st>>>(total, (unsigned)M, (unsigned)(Co / 2), K, nn_count, grad_output, gs);
+        else scale_rows_kernel<1><<<gr, 256, 0, st>>>(total, (unsigned)M, (unsigned)Co, K, nn_count, grad_output, gs);
+        SPH3D_CHECK_LAUNCH();
+    }
+    dim3 grid(p.grid_x, p.chunks);
+    const unsigned rows = (unsigned)((long long)B * N);
+#define LAUNCH_T(V, RR)                                                                                          \
+    do {                                                                                                         \
+        e = set_smem(conv_bwd_t_kernel<V, RR, 768>, p.smem);                                                     \
+        if (e != cudaSuccess) return (int)e;                                                                     \
+        conv_bwd_t_kernel<V, RR, 768><<<grid, 768, p.smem, st>>>(rows, p.rpc, (unsigned)N, (unsigned)(M + 1), F, C, g.G, \
+                                                                 seg, ent, gs, input, filter, grad_input, part); \
+    } while (0)
+    if (p.vec == 4 && r == 1) LAUNCH_T(4, 1);
+    else if (p.vec == 4 && r == 2) LAUNCH_T(4, 2);
+    else if (p.vec == 2 && r == 1) LAUNCH_T(2, 1);
+    else if (p.vec == 2 && r == 2) LAUNCH_T(2, 2);
+    else if (p.vec == 1 && r == 1) LAUNCH_T(1, 1);
+    else return (int)cudaErrorInvalidValue;
+#undef LAUNCH_T
+    SPH3D_CHECK_LAUNCH();
+    int rc = launch_reduce_partials((int)w.P, (size_t)F * Co, part, grad_filter, st);
+    if (rc) return rc;
+    *launches += 3;
+    return 0;
+}
+
+// used by conv_bwd.cu to route sph3d_depthwise_conv3d_grad
+bool bwd_transposed_supported(int B, int N, int M, int F, int C, int r, int K)
+{
+    if (tune_int("SPH3D_BWD_ALGO", 2) == 1) return false;                  // 1 = row-owned form (conv_bwd.cu), 2 = transposed
+    TPlanMain p;
+    return t_plan_main(B, N, M, F, C, r, t_geom(B, N, M, F, K), &p);
+}
+
+size_t bwd_transposed_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
+{
+    const TGeom g = t_geom(B, N, M, F, K);
+    TPlanMain p;
+    if (!t_plan_main(B, N, M, F, C, r, g, &p)) return 0;
+    return g.total + t_work(B, M, F, C, r, p).total;
+}
+
+int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const int* nn_index, const int* nn_count,
+                       const int* bin_index, const float* input, const float* filter, const float* grad_output,
+                       float* grad_input, float* grad_filter, void* workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    const TGeom g = t_geom(B, N, M, F, K);
+    TPlanMain p;
+    if (!t_plan_main(B, N, M, F, C, r, g, &p)) return (int)cudaErrorInvalidValue;
+    if (!workspace || workspace_bytes < g.total + t_work(B, M, F, C, r, p).total) return (int)cudaErrorInvalidValue;
+    char* ws = reinterpret_cast<char*>(workspace);
+    int launches = 0;
+    int rc = t_build_plan(B, N, M, F, K, g, nn_index, nn_count, bin_index, ws, st, &launches);
+    if (rc) return rc;
+    rc = t_run_main(B, N, M, F, C, r, K, g, p, ws, nn_count, input, filter, grad_output, grad_input, grad_filter,
+                    ws + g.total, st, &launches);
+    g_last_launch_count = launches;
+    return rc;
+}
+
+}  // namespace sph3d
+
+using namespace sph3d;
+
+extern "C" size_t sph3d_conv_transpose_bytes(int B, int N, int M, int F, int K)
+{
+    const TGeom g = t_geom(B, N, M, F, K);
+    return g.ok ? g.total : 0;
+}
+
+extern "C" int sph3d_conv_transpose(int B, int N, int M, int F, int K, const int* nn_index, const int* nn_count,
+                                    const int* bin_index, void* plan, size_t plan_bytes, void* stream)
+{
+    g_last_launch_count = 0;
+    const TGeom g = t_geom(B, N, M, F, K);
+    if (!g.ok || !nn_index || !nn_count || !bin_index || !plan || plan_bytes < g.total) return (int)cudaErrorInvalidValue;
+    int launches = 0;
+    int rc = t_build_plan(B, N, M, F, K, g, nn_index, nn_count, bin_index, reinterpret_cast<char*>(plan),
+                          (cudaStream_t)stream, &launches);
+    g_last_launch_count = launches;
+    return rc;
+}
+
+extern "C" size_t sph3d_depthwise_conv3d_grad_planned_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
+{
+    const TGeom g = t_geom(B, N, M, F, K);
+    TPlanMain p;
+    if (!t_plan_main(B, N, M, F, C, r, g, &p)) return 0;
+    return t_work(B, M, F, C, r, p).total;
+}
+
+extern "C" int sph3d_depthwise_conv3d_grad_planned(int B, int N, int M, int F, int C, int r, int K, const int* nn_count,
+                                                   const void* plan, size_t plan_bytes, const float* input,
+                                                   const float* filter, const float* grad_output, float* grad_input,
+                                                   float* grad_filter, void* workspace, size_t workspace_bytes, void* stream)
+{
+    g_last_launch_count = 0;
+    const TGeom g = t_geom(B, N, M, F, K);
+    TPlanMain p;
+    if (!t_plan_main(B, N, M, F, C, r, g, &p)) return (int)cudaErrorInvalidValue;
+    if (!nn_count || !plan || plan_bytes < g.total || !input || !filter || !grad_output || !grad_input || !grad_filter ||
+        !workspace || workspace_bytes < t_work(B, M, F, C, r, p).total)
+        return (int)cudaErrorInvalidValue;
+    int launches = 0;
+    int rc = t_run_main(B, N, M, F, C, r, K, g, p, reinterpret_cast<const char*>(plan), nn_count, input, filter, grad_output,
+                        grad_input, grad_filter, reinterpret_cast<char*>(workspace), (cudaStream_t)stream, &launches);
+    g_last_launch_count = launches;
+    return rc;
+}

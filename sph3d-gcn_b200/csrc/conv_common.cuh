@@ -178,6 +178,16 @@ static inline int tune_int(const char* name, int dflt)
 }
 static inline int rows_per_chunk() { return tune_int("SPH3D_ROWS_PER_CHUNK", 128); }
 
+// conv_bwd.cu: out[t] = sum_p part[p][t], fixed order (bit-reproducible)
+int launch_reduce_partials(int P, size_t n, const float* part, float* out, cudaStream_t st);
+
+// conv_bwd_t.cu: the transposed backward (default where it applies; SPH3D_BWD_ALGO=1 forces the row-owned form)
+bool bwd_transposed_supported(int B, int N, int M, int F, int C, int r, int K);
+size_t bwd_transposed_workspace_bytes(int B, int N, int M, int F, int C, int r, int K);
+int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const int* nn_index, const int* nn_count,
+                       const int* bin_index, const float* input, const float* filter, const float* grad_output,
+                       float* grad_input, float* grad_filter, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 template <typename Kern>
 static cudaError_t set_smem(Kern k, size_t bytes)
 {

@@ -54,6 +54,60 @@ def depthwise_conv3d_grad(input, filter, grad_output, nn_index, nn_count, bin_in
     return grad_input, grad_filter
 
 
+def conv_transpose(nn_index, nn_count, bin_index, num_bins, npoint):
+    """Graph-only half of the backward pass (sph3d_conv_transpose): per input point, the (output point, bin)
+    pairs that reference it, grouped by bin.  Returns an opaque int32 plan tensor for
+    depthwise_conv3d_grad_planned, or None where the planned form does not apply (num_bins > 72).  The plan
+    depends only on the graph, num_bins and npoint (points in the input cloud), so one plan serves every
+    convolution applied over that graph."""
+    nn_index = _lib.cuda_tensor(nn_index, torch.int32, 3, "nn_index")
+    nn_count = _lib.cuda_tensor(nn_count, torch.int32, 2, "nn_count")
+    bin_index = _lib.cuda_tensor(bin_index, torch.int32, 3, "bin_index")
+    if bin_index.shape != nn_index.shape or nn_count.shape != nn_index.shape[:2]:
+        raise ValueError("nn_index / nn_count / bin_index shapes are inconsistent")
+    B, M, K = nn_index.shape
+    npoint, num_bins = int(npoint), int(num_bins)
+    L = _lib.lib()
+    nbytes = L.sph3d_conv_transpose_bytes(B, npoint, M, num_bins, K)
+    if nbytes == 0:
+        return None
+    plan = torch.empty((nbytes // 4,), dtype=torch.int32, device=nn_index.device)
+    with torch.cuda.device(nn_index.device):
+        rc = L.sph3d_conv_transpose(B, npoint, M, num_bins, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
+                                    _lib.ptr(bin_index), _lib.ptr(plan), nbytes, _lib.stream_ptr())
+    _lib.check(rc, "conv_transpose")
+    return plan
+
+
+def depthwise_conv3d_grad_planned(input, filter, grad_output, nn_count, plan, nnsample):
+    """depthwise_conv3d_grad with the graph transposition hoisted out (plan from conv_transpose)."""
+    input = _lib.cuda_tensor(input, torch.float32, 3, "input")
+    filter = _lib.cuda_tensor(filter, torch.float32, 3, "filter")
+    grad_output = _lib.cuda_tensor(grad_output, torch.float32, 3, "grad_output")
+    nn_count = _lib.cuda_tensor(nn_count, torch.int32, 2, "nn_count")
+    B, N, C = input.shape
+    F, _, r = filter.shape
+    M, K = nn_count.shape[1], int(nnsample)
+    if filter.shape[1] != C:
+        raise ValueError("Input Channel size error of the filter")
+    if grad_output.shape != (B, M, C * r):
+        raise ValueError("grad_output must be (batch, mpoint, in_channels*multiplier)")
+    L = _lib.lib()
+    ws_bytes = L.sph3d_depthwise_conv3d_grad_planned_workspace_bytes(B, N, M, F, C, r, K)
+    if ws_bytes == 0 or plan is None:
+        raise ValueError("the planned gradient does not cover this shape; use depthwise_conv3d_grad")
+    grad_input = torch.empty((B, N, C), dtype=torch.float32, device=input.device)
+    grad_filter = torch.empty((F, C, r), dtype=torch.float32, device=input.device)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        rc = L.sph3d_depthwise_conv3d_grad_planned(B, N, M, F, C, r, K, _lib.ptr(nn_count), _lib.ptr(plan),
+                                                   plan.numel() * 4, _lib.ptr(input), _lib.ptr(filter),
+                                                   _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.ptr(grad_filter),
+                                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    _lib.check(rc, "depthwise_conv3d_grad_planned")
+    return grad_input, grad_filter
+
+
 class _DepthwiseConv3d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, filter, nn_index, nn_count, bin_index):

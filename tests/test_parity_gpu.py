@@ -221,6 +221,89 @@ def test_conv_zero_count_rows_and_linearity(pkg, oracle):
     assert_close(A(gi), ti, 1e-5); assert_close(A(gf), tf, 1e-5)
 
 
+def _plan_layout(B, N, M, F, K):
+    """layout of the sph3d_conv_transpose plan (csrc/conv_bwd_t.cu, t_geom): int32 words"""
+    G = -(-F // 9)
+    G = {5: 6, 7: 8}.get(G, G)
+    FP = 9 * G
+    nseg = B * N * FP
+    nseg_pad = -(-nseg // 4096) * 4096
+    a256 = lambda x: (x + 255) // 256 * 256
+    sums_off = a256(nseg_pad * 4)
+    ent_off = sums_off + a256(nseg_pad // 4096 * 4)
+    return G, FP, nseg, ent_off // 4
+
+
+TRANSPOSE_CASES = [c for c in CONV_CASES if c[0] in ("c128_r1", "c64_r2", "k156_tiles", "c6_r1_vec2")] + [
+    ("f49_default_kernel_g6", 2, 700, 48, 16, 1, (8, 2, 3)), ("f9_g1", 1, 300, 16, 8, 1, (4, 2, 1))]
+
+
+@pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
+def test_conv_transpose_plan(case, pkg, oracle):
+    """the transposed graph holds every edge exactly once, grouped by (input point, owner warp, bin), ascending m"""
+    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
+    B, N, _ = x.shape
+    M, K, F = idx.shape[1], idx.shape[2], W.shape[0]
+    cnt = cnt.copy(); cnt[:, 5::11] = 0                                   # some empty rows
+    plan = pkg.tf_conv3d.conv_transpose(T(idx), T(cnt), T(filt), F, N)
+    assert plan is not None
+    plan = A(plan)
+    G, FP, nseg, ent_w = _plan_layout(B, N, M, F, K)
+    seg_end = plan[:nseg].astype(np.int64)
+    b, m, k = np.nonzero(np.arange(K)[None, None, :] < np.minimum(cnt, K)[:, :, None])
+    n, f = idx[b, m, k].astype(np.int64), filt[b, m, k].astype(np.int64)
+    key = (b * N + n) * FP + (f % G) * 9 + f // G
+    order = np.lexsort((m, key))
+    want_entries = ((m[order].astype(np.int64) << 8) | (f[order] // G)).astype(np.uint32)
+    want_end = np.cumsum(np.bincount(key, minlength=nseg))
+    assert_equal(seg_end, want_end, case[0] + " segment ends")
+    assert_equal(plan[ent_w:ent_w + len(want_entries)].view(np.uint32), want_entries, case[0] + " entries")
+
+
+@pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
+def test_depthwise_conv3d_backward_planned(case, pkg, oracle):
+    """the split form (plan built once, reused) equals the one-call form bit for bit in grad_filter"""
+    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
+    go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
+    ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
+    plan = pkg.tf_conv3d.conv_transpose(T(idx), T(cnt), T(filt), W.shape[0], x.shape[1])
+    for rep in range(2):                                                   # the plan is not consumed by a call
+        gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad_planned(T(x), T(W), T(go), T(cnt), plan, idx.shape[2])
+        assert_close(A(gi), ti, 1e-5, case[0] + " planned grad_input")
+        assert_close(A(gf), tf, 1e-5, case[0] + " planned grad_filter")
+    gi1, gf1 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_equal(A(gf), A(gf1), case[0] + " planned vs one-call grad_filter")
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:6], ids=[c[0] for c in CONV_CASES[:6]])
+def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch):
+    """SPH3D_BWD_ALGO=1 selects the row-owned kernel of conv_bwd.cu (the fallback for F > 72): same results"""
+    monkeypatch.setenv("SPH3D_BWD_ALGO", "1")
+    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
+    go = features(66, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
+    ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
+    gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_close(A(gi), ti, 1e-5, case[0] + " row-owned grad_input")
+    assert_close(A(gf), tf, 1e-5, case[0] + " row-owned grad_filter")
+
+
+def test_conv_backward_unequal_clouds_and_garbage_padding(pkg, oracle):
+    """M != N (strided queries, as the inter-level graphs), and index slots beyond nn_count holding garbage"""
+    B, N, K, C, r = 2, 900, 32, 64, 2
+    xyz = make_cloud(67, B, N, "cube")
+    q = np.ascontiguousarray(xyz[:, ::3])
+    radius = saturating_radius(N, K)
+    idx, cnt, dst = oracle.build_sphere_neighbor(xyz, q, radius, None, K)
+    filt = oracle.spherical_kernel(xyz, q, idx, cnt, dst, radius, [8, 2, 2])
+    pad = np.arange(K)[None, None, :] >= cnt[:, :, None]
+    idx = idx.copy(); filt = filt.copy()
+    idx[pad] = 2 ** 30; filt[pad] = -7                                     # never dereferenced
+    x, W, go = features(68, B, N, C), features(69, 33, C, r), features(70, B, q.shape[1], C * r)
+    ti, tf = oracle.depthwise_conv3d_grad(x, W, go, np.where(pad, 0, idx), cnt, np.where(pad, 0, filt))
+    gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_close(A(gi), ti, 1e-5, "grad_input M != N"); assert_close(A(gf), tf, 1e-5, "grad_filter M != N")
+
+
 # ------------------------------------------------------------------------------------------ a6 FPS
 FPS_CASES = [("n1024", 3, 1024, 256, "cube"), ("n2048_p2", 2, 2048, 512, "shell"), ("n5000_p5", 2, 5000, 300, "cube"),
              ("n8192_p8", 2, 8192, 2048, "cube"), ("n10000_cs2", 2, 10000, 625, "shell"), ("n20000_cs4", 1, 20000, 200, "cube"),
