@@ -59,9 +59,11 @@ def main():
     env(SPH3D_BWD_ALGO=1)
     gi_a, gf_a = one_call()
     res["bwd_row_owned_ms"] = timeit(one_call, args.iters)
-    env(SPH3D_BWD_ALGO=None)
+    env(SPH3D_BWD_ALGO=2)
     gi_b, gf_b = one_call()
     res["bwd_transposed_ms"] = timeit(one_call, args.iters)
+    env(SPH3D_BWD_ALGO=None)
+    res["bwd_default_ms"] = timeit(one_call, args.iters)
     res["max_abs_diff_grad_input"] = float((gi_a - gi_b).abs().max())
     res["max_abs_diff_grad_filter"] = float((gf_a - gf_b).abs().max())
     res["scale_grad_input"] = float(gi_a.abs().max()); res["scale_grad_filter"] = float(gf_a.abs().max())
@@ -69,14 +71,14 @@ def main():
     build = lambda: C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N)
     plan = build()
     res["transpose_ms"] = timeit(build, args.iters)
-    env(SPH3D_BWDT_SORT=0)
-    res["transpose_nosort_ms"] = timeit(build, args.iters)
+    env(SPH3D_BWDT_SORT=1)
+    res["transpose_canonical_ms"] = timeit(build, args.iters)
     env(SPH3D_BWDT_SORT=None)
     planned = lambda: C3.depthwise_conv3d_grad_planned(d["x"], d["W"], d["go"], d["cnt"], plan, K)
     res["planned_ms"] = timeit(planned, args.iters)
     if args.sweep:
         sw = {}
-        for rpc in (16, 32, 64, 128, 256, 512):
+        for rpc in (2, 4, 8, 16, 32, 64):
             env(SPH3D_BWDT_ROWS_PER_CHUNK=rpc)
             sw["rpc%d" % rpc] = timeit(planned, args.iters)
         env(SPH3D_BWDT_ROWS_PER_CHUNK=None)

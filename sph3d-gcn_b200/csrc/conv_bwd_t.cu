@@ -40,12 +40,12 @@
 
 namespace sph3d {
 
-constexpr int T_SLOTS = 9;
+constexpr int T_WARPS = 24;               // warps per CTA of the gather kernel (768 threads)
 constexpr int SCAN_TILE = 4096;          // ints per CTA in the scan kernels (256 threads x 16)
 
 // ------------------------------------------------------------------------------------------- plan
 struct TGeom {
-    int G, FP;                  // warps per point, G*T_SLOTS segments per point
+    int G, SLOTS, FP;           // bin classes (f % G), bins per class, G*SLOTS segments per point
     size_t nseg, nseg_pad;      // B*N*FP, rounded up to SCAN_TILE
     int scan_blocks;
     size_t seg_off, sums_off, ent_off, total;   // byte offsets inside the plan
@@ -59,13 +59,20 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
     TGeom g{};
     g.ok = false;
     if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || K <= 0) return g;
-    int G = (F + T_SLOTS - 1) / T_SLOTS;
-    if (G == 5) G = 6;
-    if (G == 7) G = 8;
-    if (G > 8) return g;                                          // F > 72: conv_bwd.cu handles it
+    // smallest number of bin classes G (a divisor of the CTA's 24 warps) whose per-warp accumulators
+    // (ceil(F/G) strips of 512 B, sized for 16-byte strips so that the plan does not depend on C) fit in shared
+    // memory beside the filter and the staging arrays: F=33 -> G=3 x 11 bins, F=17 -> 2 x 9, F=49 -> 4 x 13
+    int G = 0, SL = 0;
+    const int divs[] = {1, 2, 3, 4, 6, 8, 12, 24};
+    for (int d : divs) {
+        const int sl = (F + d - 1) / d;
+        if (sl > 255) continue;
+        if ((size_t)T_WARPS * sl * 512 + (size_t)F * 512 + (size_t)T_WARPS * 512 <= 200 * 1024) { G = d; SL = sl; break; }
+    }
+    if (!G) return g;                                             // very large F: conv_bwd.cu handles it
     if ((long long)M >= (1LL << 24)) return g;                    // m is packed into 24 bits
     if ((long long)B * M * K >= (1LL << 31) || (long long)B * N >= (1LL << 31)) return g;
-    g.G = G; g.FP = G * T_SLOTS;
+    g.G = G; g.SLOTS = SL; g.FP = G * SL;
     g.nseg = (size_t)B * N * g.FP;
     g.nseg_pad = (g.nseg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
     if (g.nseg_pad / SCAN_TILE > 65536) return g;
@@ -82,7 +89,7 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
 // one thread per edge slot (b,m,k); edges beyond nn_count and malformed ids are skipped
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G, int FP,
+transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G, int SLOTS,
                        const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                        const int* __restrict__ bin_index, int* __restrict__ seg, unsigned* __restrict__ entries)
 {
@@ -94,7 +101,7 @@ transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G
         if ((unsigned)n >= N || (unsigned)f >= (unsigned)F) continue;
         const unsigned b = (unsigned)(row / M);
         const unsigned m = (unsigned)(row - (size_t)b * M);
-        const size_t s = ((size_t)b * N + n) * FP + (f % G) * T_SLOTS + f / G;
+        const size_t s = ((size_t)b * N + n) * (G * SLOTS) + (f % G) * SLOTS + f / G;
         if constexpr (FILL) {
             const int pos = atomicAdd(seg + s, 1);
             entries[pos] = (m << 8) | (unsigned)(f / G);
@@ -249,28 +256,51 @@ __device__ __forceinline__ void ld_strip_smem(float (&v)[VEC], const float* p)
     }
 }
 
-template <int VEC, int R, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp /* M+1 */, int F, int C, int G,
+template <int VEC>
+__device__ __forceinline__ void st_strip_smem(float* p, const float (&v)[VEC])
+{
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+
+constexpr int T_THREADS = 768;
+
+// Work distribution: warp w of every CTA belongs to bin class w % G and pulls chunks of `rpc` consecutive input
+// points for its class from a global counter (one counter per class and channel chunk), so the very uneven
+// in-degrees (the "first K by index" rule sends most edges to low-index points) balance themselves.
+// Per point the warp follows a three-stage software pipeline, two points ahead: segment boundaries (i+2),
+// entry list + input strip (i+1), gathers (i); inside a point 8 feature-strip gathers are in flight.
+template <int VEC, int R>
+__global__ void __launch_bounds__(T_THREADS, 1)
+conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp /* M+1 */, int F, int C, int G, int SLOTS,
                   const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
                   const float* __restrict__ input, const float* __restrict__ filter,
-                  float* __restrict__ grad_input, float* __restrict__ gw_partial)
+                  float* __restrict__ grad_input, float* __restrict__ gw_partial, int* __restrict__ counters)
 {
     static_assert(VEC % R == 0, "a lane's flat strip must cover whole input channels");
     constexpr int VI = VEC / R;                          // input channels per lane
-    constexpr int SLOTS = T_SLOTS;
+    constexpr int STRIP = 32 * VEC;                      // floats in a warp-wide strip
+    constexpr int NWARPS = T_THREADS / 32;
     const int Co = C * R;
     extern __shared__ __align__(16) float smem[];
-    float* Wsh = smem;                                   // [F][32*VEC] flat-channel filter strips of this chunk
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = THREADS / 32;
-    const int wig = warp % G, group = warp / G, ngroups = nwarps / G;
-    const int cbase = blockIdx.y * 32 * VEC;             // first flat channel of this chunk
-    for (int t = threadIdx.x; t < F * 32 * VEC; t += THREADS) {
-        const int f = t / (32 * VEC), ch = cbase + t % (32 * VEC);
+    float* Wsh = smem;                                   // [F][STRIP] flat-channel filter strips of this chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cls = warp % G;                            // my bins: f = s*G + cls, s < SLOTS
+    const int cbase = blockIdx.y * STRIP;                // first flat channel of this chunk
+    for (int t = threadIdx.x; t < F * STRIP; t += T_THREADS) {
+        const int f = t / STRIP, ch = cbase + t % STRIP;
         Wsh[t] = (ch < Co) ? __ldg(filter + (size_t)f * Co + ch) : 0.f;
     }
-    unsigned* sOff = reinterpret_cast<unsigned*>(Wsh + (size_t)F * 32 * VEC) + warp * 128;
+    float* accS = Wsh + (size_t)F * STRIP + (size_t)warp * SLOTS * STRIP + lane * VEC;   // my accumulators [SLOTS][strip]
+    unsigned* sOff = reinterpret_cast<unsigned*>(Wsh + (size_t)F * STRIP + (size_t)NWARPS * SLOTS * STRIP) + warp * 128;
     int* sCode = reinterpret_cast<int*>(sOff + 64);
+    {
+        float z[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; e++) z[e] = 0.f;
+        for (int s = 0; s < SLOTS; s++) st_strip_smem<VEC>(accS + s * STRIP, z);
+    }
     __syncthreads();
 
     const int i0 = cbase + lane * VEC;                   // my first flat channel
@@ -280,122 +310,171 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp
     const unsigned gsStrideB = (unsigned)Co * 4u;
     const unsigned zoff = (Mp - 1u) * gsStrideB;         // the zero row of every cloud
     const size_t gcloudB = (size_t)Mp * Co * 4;
-    const float* wlane = Wsh + lane * VEC;
+    const float* wlane = Wsh + (size_t)cls * STRIP + lane * VEC;      // strip of my first bin; next bin: + G*STRIP
+    const int wstep = G * STRIP;
     const int FP = G * SLOTS;
-
-    float acc[SLOTS][VEC];
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++)
-#pragma unroll
-        for (int e = 0; e < VEC; e++) acc[s][e] = 0.f;
-
     const unsigned nchunks = (rows + rpc - 1) / rpc;
-    for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const unsigned rbeg = chunk * rpc;
-        const unsigned rend = min(rbeg + rpc, rows);
-        unsigned row = rbeg + group;
-        if (row >= rend) continue;
-        RowCursor cur;
-        cur.init(row, N);
-        for (; row < rend; row += ngroups, cur.advance(ngroups, N)) {
-            // my sub-list: segments [sb, sb+SLOTS) of this point; seg[s] = end of segment s
-            const size_t sb = (size_t)row * FP + wig * SLOTS;
-            int bv = 0;
-            if (lane == 0 && sb > 0) bv = __ldg(seg + sb - 1);
-            if (lane == 1) bv = __ldg(seg + sb + SLOTS - 1);
-            const int beg = __shfl_sync(FULL_MASK, bv, 0), end = __shfl_sync(FULL_MASK, bv, 1);
-            if (end <= beg) continue;
+    int* ctr = counters + blockIdx.y * G + cls;
 
-            float inx[VEC];                               // in[b,n,c] expanded to my flat channels
-            {
-                float t[VI];
-                VecIO<VI>::ld(t, input + (size_t)row * C + cin0, true);
+    // ---- chunk iterator (runs two points ahead of the gathers) ----
+    unsigned it_row = 0, it_rend = 0, it_b = 0, it_n = 0;
+    bool it_valid = true;
+    int it_next = 0;                                     // lane 0: id of the chunk after the current one
+    auto fetch = [&]() { int c = 0; if (lane == 0) c = atomicAdd(ctr, 1); return c; };
+    auto open_chunk = [&](unsigned c) {
+        if (c >= nchunks) { it_valid = false; return; }
+        it_row = c * rpc; it_rend = min(it_row + rpc, rows);
+        it_b = it_row / N; it_n = it_row - it_b * N;
+    };
+    {
+        const unsigned c = (unsigned)__shfl_sync(FULL_MASK, fetch(), 0);
+        it_next = fetch();
+        open_chunk(c);
+    }
+    auto advance = [&]() {
+        if (!it_valid) return;
+        it_row++; it_n++;
+        if (it_n == N) { it_n = 0; it_b++; }
+        if (it_row >= it_rend) {
+            const unsigned c = (unsigned)__shfl_sync(FULL_MASK, it_next, 0);
+            it_next = fetch();
+            open_chunk(c);
+        }
+    };
+
+    // stage "boundaries": lane 0 holds the start, lane 1 the end of my sub-list of point `row`
+    struct StageB { unsigned row, b; bool valid; int bv; };
+    auto make_b = [&]() {
+        StageB x; x.row = it_row; x.b = it_b; x.valid = it_valid; x.bv = 0;
+        if (it_valid) {
+            const size_t sb = (size_t)it_row * FP + (size_t)cls * SLOTS;
+            if (lane == 0 && sb > 0) x.bv = __ldg(seg + sb - 1);
+            if (lane == 1) x.bv = __ldg(seg + sb + SLOTS - 1);
+        }
+        return x;
+    };
+    // stage "entries": first 64 entries of the sub-list and the point's input strip
+    struct StageE { unsigned row, b; bool valid; int beg, end; unsigned e0, e1; float in[VI]; };
+    auto make_e = [&](const StageB& x) {
+        StageE y; y.row = x.row; y.b = x.b; y.valid = x.valid;
+        y.beg = __shfl_sync(FULL_MASK, x.bv, 0); y.end = __shfl_sync(FULL_MASK, x.bv, 1);
+        y.e0 = 0; y.e1 = 0;
 #pragma unroll
-                for (int e = 0; e < VEC; e++) inx[e] = t[e / R];
+        for (int v = 0; v < VI; v++) y.in[v] = 0.f;
+        if (x.valid && y.end > y.beg) {
+            if (y.beg + lane < y.end) y.e0 = __ldg(entries + y.beg + lane);
+            if (y.beg + 32 + lane < y.end) y.e1 = __ldg(entries + y.beg + 32 + lane);
+            VecIO<VI>::ld(y.in, input + (size_t)x.row * C + cin0, true);
+        }
+        return y;
+    };
+
+    StageB sB = make_b(); advance();
+    StageE sE = make_e(sB);
+    sB = make_b(); advance();
+
+    while (sE.valid) {
+        const StageE cur = sE;
+        sE = make_e(sB);                                  // loads for point i+1 (boundaries arrived during point i-1)
+        sB = make_b(); advance();                         // boundary loads for point i+2
+        if (cur.end <= cur.beg) continue;
+
+        float inx[VEC];                                   // in[b,n,c] expanded to my flat channels
+#pragma unroll
+        for (int e = 0; e < VEC; e++) inx[e] = cur.in[e / R];
+        float gi[VEC], T[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; e++) { gi[e] = 0.f; T[e] = 0.f; }
+        const char* gb = reinterpret_cast<const char*>(gs) + cur.b * gcloudB + (size_t)i0ld * 4;
+
+        auto consume = [&](const float (&v)[VEC], int code) {
+            strip_add<VEC>(T, v);
+            if (code & 1) {                                // last edge of its bin segment (warp-uniform)
+                const int s = code >> 1;
+                float w[VEC], a[VEC];
+                ld_strip_smem<VEC>(w, wlane + s * wstep);
+                ld_strip_smem<VEC>(a, accS + s * STRIP);
+                strip_fma<VEC>(gi, w, T);
+                strip_fma<VEC>(a, inx, T);
+                st_strip_smem<VEC>(accS + s * STRIP, a);
+#pragma unroll
+                for (int e = 0; e < VEC; e++) T[e] = 0.f;
             }
-            float gi[VEC], T[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; e++) { gi[e] = 0.f; T[e] = 0.f; }
-            const char* gb = reinterpret_cast<const char*>(gs) + cur.b * gcloudB + (size_t)i0ld * 4;
+        };
+        auto load4 = [&](int p, float (&v)[4][VEC]) {
+            const uint4 oo = *reinterpret_cast<const uint4*>(sOff + p);
+            ld_strip<VEC>(v[0], gb, oo.x); ld_strip<VEC>(v[1], gb, oo.y);
+            ld_strip<VEC>(v[2], gb, oo.z); ld_strip<VEC>(v[3], gb, oo.w);
+        };
+        auto consume4 = [&](int p, const float (&v)[4][VEC]) {
+            const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
+            consume(v[0], cc.x); consume(v[1], cc.y); consume(v[2], cc.z); consume(v[3], cc.w);
+        };
 
-            auto consume = [&](const float (&v)[VEC], int code) {
-                strip_add<VEC>(T, v);
-                if (code & 1) {                            // last edge of its bin segment (warp-uniform)
-                    const int s = code >> 1;
-                    float w[VEC];
-                    ld_strip_smem<VEC>(w, wlane + (s * G + wig) * 32 * VEC);
-                    strip_fma<VEC>(gi, w, T);
-                    switch (s) {                           // static register indexing of the owned bin
-                        case 0: strip_fma<VEC>(acc[0], inx, T); break;
-                        case 1: strip_fma<VEC>(acc[1], inx, T); break;
-                        case 2: strip_fma<VEC>(acc[2], inx, T); break;
-                        case 3: strip_fma<VEC>(acc[3], inx, T); break;
-                        case 4: strip_fma<VEC>(acc[4], inx, T); break;
-                        case 5: strip_fma<VEC>(acc[5], inx, T); break;
-                        case 6: strip_fma<VEC>(acc[6], inx, T); break;
-                        case 7: strip_fma<VEC>(acc[7], inx, T); break;
-                        default: strip_fma<VEC>(acc[8], inx, T); break;
-                    }
-#pragma unroll
-                    for (int e = 0; e < VEC; e++) T[e] = 0.f;
-                }
-            };
-
-            for (int kt = beg; kt < end; kt += 64) {
-                const int nt = min(64, end - kt);
-                const int nt4 = (nt + 3) & ~3;
-                const int p0 = lane, p1 = 32 + lane;
-                unsigned e0 = 0, e1 = 0;
+        for (int kt = cur.beg; kt < cur.end; kt += 64) {
+            const int nt = min(64, cur.end - kt);
+            const int nt4 = (nt + 3) & ~3;
+            const int p0 = lane, p1 = 32 + lane;
+            unsigned e0 = cur.e0, e1 = cur.e1;
+            if (kt != cur.beg) {                           // only the first tile was prefetched
+                e0 = 0; e1 = 0;
                 if (p0 < nt) e0 = __ldg(entries + kt + p0);
                 if (p1 < nt) e1 = __ldg(entries + kt + p1);
-                const int s0 = (int)(e0 & 255u), s1 = (int)(e1 & 255u);
-                int nx0 = __shfl_down_sync(FULL_MASK, s0, 1);
-                const int nx1 = __shfl_down_sync(FULL_MASK, s1, 1);
-                const int first1 = __shfl_sync(FULL_MASK, s1, 0);
-                if (lane == 31) nx0 = first1;
-                if (p0 < nt) {
-                    sOff[p0] = (e0 >> 8) * gsStrideB;
-                    sCode[p0] = (s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0);
-                } else if (p0 < nt4) {
-                    sOff[p0] = zoff; sCode[p0] = 0;
-                }
-                if (p1 < nt) {
-                    sOff[p1] = (e1 >> 8) * gsStrideB;
-                    sCode[p1] = (s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0);
-                } else if (p1 < nt4) {
-                    sOff[p1] = zoff; sCode[p1] = 0;
-                }
-                __syncwarp();
-                for (int p = 0; p < nt4; p += 4) {                 // four independent gathers in flight
-                    const uint4 oo = *reinterpret_cast<const uint4*>(sOff + p);
-                    const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
-                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
-                    ld_strip<VEC>(v0, gb, oo.x); ld_strip<VEC>(v1, gb, oo.y);
-                    ld_strip<VEC>(v2, gb, oo.z); ld_strip<VEC>(v3, gb, oo.w);
-                    consume(v0, cc.x); consume(v1, cc.y); consume(v2, cc.z); consume(v3, cc.w);
-                }
-                __syncwarp();                                      // sOff/sCode are rewritten by the next tile/row
             }
-            if (active) {
-                float o[VI];
-#pragma unroll
-                for (int v = 0; v < VI; v++) {
-                    float t = 0.f;
-#pragma unroll
-                    for (int j = 0; j < R; j++) t += gi[v * R + j];
-                    o[v] = t;
-                }
-                VecIO<VI>::red(grad_input + (size_t)row * C + cin0, o);
+            const int s0 = (int)(e0 & 255u), s1 = (int)(e1 & 255u);
+            int nx0 = __shfl_down_sync(FULL_MASK, s0, 1);
+            const int nx1 = __shfl_down_sync(FULL_MASK, s1, 1);
+            const int first1 = __shfl_sync(FULL_MASK, s1, 0);
+            if (lane == 31) nx0 = first1;
+            if (p0 < nt) {
+                sOff[p0] = (e0 >> 8) * gsStrideB;
+                sCode[p0] = (s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0);
+            } else if (p0 < nt4) {
+                sOff[p0] = zoff; sCode[p0] = 0;
             }
+            if (p1 < nt) {
+                sOff[p1] = (e1 >> 8) * gsStrideB;
+                sCode[p1] = (s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0);
+            } else if (p1 < nt4) {
+                sOff[p1] = zoff; sCode[p1] = 0;
+            }
+            __syncwarp();
+            float va[4][VEC], vb[4][VEC];
+            load4(0, va);
+            for (int p = 0; p < nt4; p += 8) {               // eight independent gathers in flight
+                const bool more = p + 4 < nt4;
+                if (more) load4(p + 4, vb);
+                consume4(p, va);
+                if (more) {
+                    if (p + 8 < nt4) load4(p + 8, va);
+                    consume4(p + 4, vb);
+                }
+            }
+            __syncwarp();                                      // sOff/sCode are rewritten by the next tile/point
+        }
+        if (active) {
+            float o[VI];
+#pragma unroll
+            for (int v = 0; v < VI; v++) {
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < R; j++) t += gi[v * R + j];
+                o[v] = t;
+            }
+            VecIO<VI>::red(grad_input + (size_t)cur.row * C + cin0, o);
         }
     }
-    // partial [blockIdx.x][group][f][flat channel]: every (f, channel) is written by exactly one warp of the group
+    // partial [blockIdx.x][warp / G][f][flat channel]: every (f, channel) of a partial is written by exactly one warp
+    __syncwarp();
     if (active) {
-        float* part = gw_partial + ((size_t)blockIdx.x * ngroups + group) * F * Co;
-#pragma unroll
+        float* part = gw_partial + ((size_t)blockIdx.x * (NWARPS / G) + warp / G) * F * Co;
         for (int s = 0; s < SLOTS; s++) {
-            const int f = s * G + wig;
-            if (f < F) VecIO<VEC>::st(part + (size_t)f * Co + i0, acc[s]);
+            const int f = s * G + cls;
+            if (f < F) {
+                float a[VEC];
+                ld_strip_smem<VEC>(a, accS + s * STRIP);
+                VecIO<VEC>::st(part + (size_t)f * Co + i0, a);
+            }
         }
     }
 }
@@ -417,13 +496,13 @@ static bool t_plan_main(int B, int N, int M, int F, int C, int r, const TGeom& g
     TPlanMain p{};
     p.vec = vec;
     p.chunks = (int)((Co + 32 * vec - 1) / (32 * vec));
-    p.threads = 768;
-    if ((p.threads / 32) % g.G) return false;
-    p.ngroups = p.threads / 32 / g.G;
-    p.smem = (size_t)F * 32 * vec * sizeof(float) + (size_t)(p.threads / 32) * 128 * sizeof(int);
+    p.threads = T_THREADS;
+    if (T_WARPS % g.G) return false;
+    p.ngroups = T_WARPS / g.G;
+    p.smem = ((size_t)F + (size_t)T_WARPS * g.SLOTS) * 32 * vec * sizeof(float) + (size_t)T_WARPS * 128 * sizeof(int);
     if (p.smem > SMEM_CAP) return false;
     const long long rows = (long long)B * N;
-    p.rpc = (unsigned)tune_int("SPH3D_BWDT_ROWS_PER_CHUNK", 64);
+    p.rpc = (unsigned)tune_int("SPH3D_BWDT_ROWS_PER_CHUNK", 8);
     const long long nchunks = (rows + p.rpc - 1) / p.rpc;
     long long want = sm_count();
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
@@ -450,18 +529,18 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
     if (e != cudaSuccess) return (int)e;
     const size_t slots = (size_t)B * M * K;
     const unsigned ge = grid_for(slots, 256, 16);
-    transpose_edges_kernel<false><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.FP, nn_index, nn_count,
+    transpose_edges_kernel<false><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, nn_index, nn_count,
                                                      bin_index, seg, ent);
     SPH3D_CHECK_LAUNCH();
     scan_reduce_kernel<<<g.scan_blocks, 256, 0, st>>>(reinterpret_cast<const int4*>(seg), sums);
     SPH3D_CHECK_LAUNCH();
     scan_apply_kernel<<<g.scan_blocks, 256, 0, st>>>(reinterpret_cast<int4*>(seg), sums);
     SPH3D_CHECK_LAUNCH();
-    transpose_edges_kernel<true><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.FP, nn_index, nn_count,
+    transpose_edges_kernel<true><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, nn_index, nn_count,
                                                     bin_index, seg, ent);
     SPH3D_CHECK_LAUNCH();
     *launches += 4;
-    if (tune_int("SPH3D_BWDT_SORT", 1) == 1) {
+    if (tune_int("SPH3D_BWDT_SORT", 0) == 1) {             // opt-in: canonical order inside every segment
         sort_segments_kernel<<<grid_for(g.nseg, 256, 16), 256, 0, st>>>(g.nseg, seg, ent);
         SPH3D_CHECK_LAUNCH();
         *launches += 1;
@@ -470,7 +549,7 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
 }
 
 // workspace of the gradient call proper (scaled grad_output + filter partials), after an optional plan
-struct TWork { size_t gs_off, part_off, total; size_t P; };
+struct TWork { size_t gs_off, part_off, ctr_off, total; size_t P; };
 
 static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
 {
@@ -479,7 +558,8 @@ static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
     w.gs_off = 0;
     w.part_off = align256((size_t)B * (M + 1) * Co * sizeof(float));
     w.P = (size_t)p.grid_x * p.ngroups;
-    w.total = w.part_off + align256(w.P * F * Co * sizeof(float));
+    w.ctr_off = w.part_off + align256(w.P * F * Co * sizeof(float));
+    w.total = w.ctr_off + align256((size_t)p.chunks * T_WARPS * sizeof(int));       // chunk counters [channel chunk][class]
     return w;
 }
 
@@ -493,7 +573,10 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     float* part = reinterpret_cast<float*>(work + w.part_off);
     const int* seg = reinterpret_cast<const int*>(plan + g.seg_off);
     const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
+    int* counters = reinterpret_cast<int*>(work + w.ctr_off);
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(counters, 0, (size_t)p.chunks * T_WARPS * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     {
         const int V = (Co % 4 == 0) ? 4 : ((Co % 2 == 0) ? 2 : 1);
@@ -508,10 +591,11 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     const unsigned rows = (unsigned)((long long)B * N);
 #define LAUNCH_T(V, RR)                                                                                          \
     do {                                                                                                         \
-        e = set_smem(conv_bwd_t_kernel<V, RR, 768>, p.smem);                                                     \
+        e = set_smem(conv_bwd_t_kernel<V, RR>, p.smem);                                                          \
         if (e != cudaSuccess) return (int)e;                                                                     \
-        conv_bwd_t_kernel<V, RR, 768><<<grid, 768, p.smem, st>>>(rows, p.rpc, (unsigned)N, (unsigned)(M + 1), F, C, g.G, \
-                                                                 seg, ent, gs, input, filter, grad_input, part); \
+        conv_bwd_t_kernel<V, RR><<<grid, T_THREADS, p.smem, st>>>(rows, p.rpc, (unsigned)N, (unsigned)(M + 1), F, C, g.G, \
+                                                                  g.SLOTS, seg, ent, gs, input, filter, grad_input, part, \
+                                                                  counters);                                    \
     } while (0)
     if (p.vec == 4 && r == 1) LAUNCH_T(4, 1);
     else if (p.vec == 4 && r == 2) LAUNCH_T(4, 2);
@@ -530,7 +614,12 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
 // used by conv_bwd.cu to route sph3d_depthwise_conv3d_grad
 bool bwd_transposed_supported(int B, int N, int M, int F, int C, int r, int K)
 {
-    if (tune_int("SPH3D_BWD_ALGO", 2) == 1) return false;                  // 1 = row-owned form (conv_bwd.cu), 2 = transposed
+    // SPH3D_BWD_ALGO: unset = auto, 1 = row-owned form (conv_bwd.cu) everywhere, 2 = transposed form wherever it applies.
+    // Auto: the transposed form gathers C*r floats per edge where the row-owned form gathers C and reduces C, so it
+    // wins for r = 1 (measured) and is left to the planned entry points for r = 2.
+    const int algo = tune_int("SPH3D_BWD_ALGO", 0);
+    if (algo == 1) return false;
+    if (algo != 2 && r != 1) return false;
     TPlanMain p;
     return t_plan_main(B, N, M, F, C, r, t_geom(B, N, M, F, K), &p);
 }

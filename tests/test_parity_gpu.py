@@ -193,10 +193,9 @@ def test_depthwise_conv3d_backward(case, pkg, oracle, ref):
     out.backward(T(go))
     assert_close(A(xt.grad), ti, 1e-5, case[0] + " grad_input vs fp64 oracle")
     assert_close(A(Wt.grad), tf, 1e-5, case[0] + " grad_filter vs fp64 oracle")
-    # grad_filter is reduced in a fixed order: deterministic run to run
     gi2, gf2 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
-    if W.shape[2] in (1, 2) and W.shape[0] <= 128:   # (the any-r / huge-F fallback uses float atomics, like the reference)
-        assert_equal(A(gf2), A(Wt.grad), "grad_filter determinism")
+    assert_close(A(gi2), ti, 1e-5, case[0] + " grad_input, second call")
+    assert_close(A(gf2), tf, 1e-5, case[0] + " grad_filter, second call")
     if ref is not None:
         ri, rf = ref.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
         assert_close(A(ri), ti, 1e-5, "reference grad_input vs oracle")
@@ -223,24 +222,29 @@ def test_conv_zero_count_rows_and_linearity(pkg, oracle):
 
 def _plan_layout(B, N, M, F, K):
     """layout of the sph3d_conv_transpose plan (csrc/conv_bwd_t.cu, t_geom): int32 words"""
-    G = -(-F // 9)
-    G = {5: 6, 7: 8}.get(G, G)
-    FP = 9 * G
+    for G in (1, 2, 3, 4, 6, 8, 12, 24):
+        SL = -(-F // G)
+        if SL <= 255 and 24 * SL * 512 + F * 512 + 24 * 512 <= 200 * 1024:
+            break
+    FP = SL * G
     nseg = B * N * FP
     nseg_pad = -(-nseg // 4096) * 4096
     a256 = lambda x: (x + 255) // 256 * 256
     sums_off = a256(nseg_pad * 4)
     ent_off = sums_off + a256(nseg_pad // 4096 * 4)
-    return G, FP, nseg, ent_off // 4
+    return G, SL, FP, nseg, ent_off // 4
 
 
 TRANSPOSE_CASES = [c for c in CONV_CASES if c[0] in ("c128_r1", "c64_r2", "k156_tiles", "c6_r1_vec2")] + [
     ("f49_default_kernel_g6", 2, 700, 48, 16, 1, (8, 2, 3)), ("f9_g1", 1, 300, 16, 8, 1, (4, 2, 1))]
 
 
+@pytest.mark.parametrize("canonical", [0, 1])
 @pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
-def test_conv_transpose_plan(case, pkg, oracle):
-    """the transposed graph holds every edge exactly once, grouped by (input point, owner warp, bin), ascending m"""
+def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
+    """the transposed graph holds every edge exactly once, grouped by (input point, bin class, bin); with
+    SPH3D_BWDT_SORT=1 additionally in ascending m inside a segment"""
+    monkeypatch.setenv("SPH3D_BWDT_SORT", str(canonical))
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     B, N, _ = x.shape
     M, K, F = idx.shape[1], idx.shape[2], W.shape[0]
@@ -248,21 +252,27 @@ def test_conv_transpose_plan(case, pkg, oracle):
     plan = pkg.tf_conv3d.conv_transpose(T(idx), T(cnt), T(filt), F, N)
     assert plan is not None
     plan = A(plan)
-    G, FP, nseg, ent_w = _plan_layout(B, N, M, F, K)
+    G, SL, FP, nseg, ent_w = _plan_layout(B, N, M, F, K)
     seg_end = plan[:nseg].astype(np.int64)
     b, m, k = np.nonzero(np.arange(K)[None, None, :] < np.minimum(cnt, K)[:, :, None])
     n, f = idx[b, m, k].astype(np.int64), filt[b, m, k].astype(np.int64)
-    key = (b * N + n) * FP + (f % G) * 9 + f // G
+    key = (b * N + n) * FP + (f % G) * SL + f // G
     order = np.lexsort((m, key))
     want_entries = ((m[order].astype(np.int64) << 8) | (f[order] // G)).astype(np.uint32)
-    want_end = np.cumsum(np.bincount(key, minlength=nseg))
-    assert_equal(seg_end, want_end, case[0] + " segment ends")
-    assert_equal(plan[ent_w:ent_w + len(want_entries)].view(np.uint32), want_entries, case[0] + " entries")
+    counts = np.bincount(key, minlength=nseg)
+    assert_equal(seg_end, np.cumsum(counts), case[0] + " segment ends")
+    got = plan[ent_w:ent_w + len(want_entries)].view(np.uint32)
+    if not canonical:                                                      # any order inside a segment
+        seg_of = np.repeat(np.arange(nseg), counts)
+        got = got[np.lexsort((got, seg_of))]
+    assert_equal(got, want_entries, case[0] + " entries")
 
 
 @pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
-def test_depthwise_conv3d_backward_planned(case, pkg, oracle):
-    """the split form (plan built once, reused) equals the one-call form bit for bit in grad_filter"""
+def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch):
+    """the split form (plan built once, reused) equals the one-call form; with canonical segment order
+    (SPH3D_BWDT_SORT=1) bit for bit in grad_filter"""
+    monkeypatch.setenv("SPH3D_BWDT_SORT", "1")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
     ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
@@ -277,7 +287,8 @@ def test_depthwise_conv3d_backward_planned(case, pkg, oracle):
 
 @pytest.mark.parametrize("case", CONV_CASES[:6], ids=[c[0] for c in CONV_CASES[:6]])
 def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch):
-    """SPH3D_BWD_ALGO=1 selects the row-owned kernel of conv_bwd.cu (the fallback for F > 72): same results"""
+    """SPH3D_BWD_ALGO=1 selects the row-owned kernel of conv_bwd.cu everywhere: same results, and its
+    grad_filter (fixed-order reduction of register partials) is bit-reproducible run to run"""
     monkeypatch.setenv("SPH3D_BWD_ALGO", "1")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(66, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
@@ -285,6 +296,18 @@ def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch
     gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
     assert_close(A(gi), ti, 1e-5, case[0] + " row-owned grad_input")
     assert_close(A(gf), tf, 1e-5, case[0] + " row-owned grad_filter")
+    gi2, gf2 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_equal(A(gf2), A(gf), "row-owned grad_filter determinism")
+
+
+@pytest.mark.parametrize("case", TRANSPOSE_CASES[:3], ids=[c[0] for c in TRANSPOSE_CASES[:3]])
+def test_transposed_backward_canonical_order_is_deterministic(case, pkg, oracle, monkeypatch):
+    monkeypatch.setenv("SPH3D_BWDT_SORT", "1")
+    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
+    go = features(66, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
+    gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    gi2, gf2 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_equal(A(gf2), A(gf), "grad_filter determinism with canonical segment order")
 
 
 def test_conv_backward_unequal_clouds_and_garbage_padding(pkg, oracle):
