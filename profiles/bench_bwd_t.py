@@ -78,10 +78,12 @@ def main():
     res["planned_ms"] = timeit(planned, args.iters)
     if args.sweep:
         sw = {}
-        for rpc in (2, 4, 8, 16, 32, 64):
-            env(SPH3D_BWDT_ROWS_PER_CHUNK=rpc)
-            sw["rpc%d" % rpc] = timeit(planned, args.iters)
-        env(SPH3D_BWDT_ROWS_PER_CHUNK=None)
+        for name, kw in (("768thr_g4", dict(SPH3D_BWDT_G=4)), ("1024thr", dict(SPH3D_BWDT_THREADS=1024)),
+                         ("1024thr_g8", dict(SPH3D_BWDT_THREADS=1024, SPH3D_BWDT_G=8))):
+            env(**kw)
+            plan2 = build()                                   # the plan geometry follows the launch configuration
+            sw[name] = timeit(lambda: C3.depthwise_conv3d_grad_planned(d["x"], d["W"], d["go"], d["cnt"], plan2, K), args.iters)
+            env(**{k: None for k in kw})
         res["planned_sweep_ms"] = sw
     print(json.dumps(res))
     if args.out:

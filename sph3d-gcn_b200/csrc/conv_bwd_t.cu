@@ -40,7 +40,9 @@
 
 namespace sph3d {
 
-constexpr int T_WARPS = 24;               // warps per CTA of the gather kernel (768 threads)
+// warps per CTA of the gather kernel: 24 (768 threads, 80 registers, 8 gathers in flight per warp; default) or
+// 32 (SPH3D_BWDT_THREADS=1024: 64 registers, 4 in flight)
+static inline int t_warps() { return tune_int("SPH3D_BWDT_THREADS", 768) == 1024 ? 32 : 24; }
 constexpr int SCAN_TILE = 4096;          // ints per CTA in the scan kernels (256 threads x 16)
 
 // ------------------------------------------------------------------------------------------- plan
@@ -59,19 +61,21 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
     TGeom g{};
     g.ok = false;
     if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || K <= 0) return g;
-    // smallest number of bin classes G (a divisor of the CTA's 24 warps) whose per-warp accumulators
+    // smallest number of bin classes G (a divisor of the CTA's warp count) whose per-warp accumulators
     // (ceil(F/G) strips of 512 B, sized for 16-byte strips so that the plan does not depend on C) fit in shared
     // memory beside the filter and the staging arrays: F=33 -> G=3 x 11 bins, F=17 -> 2 x 9, F=49 -> 4 x 13
     int G = 0, SL = 0;
-    const int divs[] = {1, 2, 3, 4, 6, 8, 12, 24};
-    for (int d : divs) {
+    const int nw = t_warps();
+    const int g_min = tune_int("SPH3D_BWDT_G", 1);
+    for (int d = g_min; d <= nw; d++) {
+        if (nw % d) continue;
         const int sl = (F + d - 1) / d;
-        if (sl > 255) continue;
-        if ((size_t)T_WARPS * sl * 512 + (size_t)F * 512 + (size_t)T_WARPS * 512 <= 200 * 1024) { G = d; SL = sl; break; }
+        if (sl > 127) continue;
+        if ((size_t)nw * sl * 512 + (size_t)F * 512 + (size_t)nw * 512 <= 210 * 1024) { G = d; SL = sl; break; }
     }
     if (!G) return g;                                             // very large F: conv_bwd.cu handles it
-    if ((long long)M >= (1LL << 24)) return g;                    // m is packed into 24 bits
-    if ((long long)B * M * K >= (1LL << 31) || (long long)B * N >= (1LL << 31)) return g;
+    if ((long long)B * M >= (1LL << 24)) return g;                // the output row b*M+m is packed into 24 bits
+    if ((long long)B * M * K >= (1LL << 31) || (long long)B * N * G * SL >= (1LL << 31)) return g;
     g.G = G; g.SLOTS = SL; g.FP = G * SL;
     g.nseg = (size_t)B * N * g.FP;
     g.nseg_pad = (g.nseg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
@@ -100,11 +104,10 @@ transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G
         const int n = __ldg(nn_index + t), f = __ldg(bin_index + t);
         if ((unsigned)n >= N || (unsigned)f >= (unsigned)F) continue;
         const unsigned b = (unsigned)(row / M);
-        const unsigned m = (unsigned)(row - (size_t)b * M);
         const size_t s = ((size_t)b * N + n) * (G * SLOTS) + (f % G) * SLOTS + f / G;
         if constexpr (FILL) {
             const int pos = atomicAdd(seg + s, 1);
-            entries[pos] = (m << 8) | (unsigned)(f / G);
+            entries[pos] = ((unsigned)row << 8) | (unsigned)(f / G);     // row = b*M + m: the row of gs this edge gathers
         } else {
             atomicAdd(seg + s, 1);                                  // result unused: RED.ADD
         }
@@ -198,26 +201,22 @@ sort_segments_kernel(size_t nseg, const int* __restrict__ seg, unsigned* __restr
     }
 }
 
-// gs[b, m, :] = gO[b, m, :] / cnt[b, m]   (m < M);   gs[b, M, :] = 0      -- gs is (B, M+1, Co)
+// gs[row, :] = gO[row, :] / cnt[row]   (row = b*M + m < B*M);   gs[B*M, :] = 0      -- gs is (B*M + 1, Co)
 template <int V>
 __global__ void __launch_bounds__(256)
-scale_rows_kernel(size_t total /* B*(M+1)*Co/V */, unsigned M, unsigned CoV, int K, const int* __restrict__ nn_count,
-                  const float* __restrict__ go, float* __restrict__ gs)
+scale_rows_kernel(size_t total /* (B*M+1)*Co/V */, size_t rows /* B*M */, unsigned CoV, int K,
+                  const int* __restrict__ nn_count, const float* __restrict__ go, float* __restrict__ gs)
 {
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t rowp = t / CoV;
-        const unsigned i = (unsigned)(t - rowp * CoV);
-        const unsigned b = (unsigned)(rowp / (M + 1));
-        const unsigned m = (unsigned)(rowp - (size_t)b * (M + 1));
+        const size_t row = t / CoV;
         float v[V];
 #pragma unroll
         for (int u = 0; u < V; u++) v[u] = 0.f;
-        if (m < M) {
-            const size_t row = (size_t)b * M + m;
+        if (row < rows) {
             const int cnt = min(__ldg(nn_count + row), K);
             if (cnt > 0) {
                 const float inv = 1.0f / (float)cnt;
-                VecIO<V>::ld(v, go + (row * CoV + i) * V, true);
+                VecIO<V>::ld(v, go + t * V, true);
 #pragma unroll
                 for (int u = 0; u < V; u++) v[u] *= inv;
             }
@@ -264,31 +263,31 @@ __device__ __forceinline__ void st_strip_smem(float* p, const float (&v)[VEC])
     else *p = v[0];
 }
 
-constexpr int T_THREADS = 768;
-
-// Work distribution: warp w of every CTA belongs to bin class w % G and pulls chunks of `rpc` consecutive input
-// points for its class from a global counter (one counter per class and channel chunk), so the very uneven
-// in-degrees (the "first K by index" rule sends most edges to low-index points) balance themselves.
-// Per point the warp follows a three-stage software pipeline, two points ahead: segment boundaries (i+2),
-// entry list + input strip (i+1), gathers (i); inside a point 8 feature-strip gathers are in flight.
-template <int VEC, int R>
-__global__ void __launch_bounds__(T_THREADS, 1)
-conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp /* M+1 */, int F, int C, int G, int SLOTS,
+// Work distribution: warp w of every CTA belongs to bin class w % G; the warps of a class take the input points
+// round-robin (point = slot, slot + W, ... with W = warps of that class in the grid).  The in-degrees are very
+// uneven (the "first K by index" rule sends most edges to the low-index points of every cloud) but each warp's
+// points are an even sample of all of them, so the static split balances, all warps sweep the batch cloud by
+// cloud together (the gathered cloud stays L2-resident), and the assignment is reproducible.
+// Per point the warp runs a three-stage software pipeline, two points ahead: segment boundaries (i+2), entry
+// list + input strip (i+1), gathers (i); inside a point 4*DEPTH feature-strip gathers are in flight.
+template <int VEC, int R, int THREADS, int DEPTH>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of gs */, int F, int C, int G, int SLOTS,
                   const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
                   const float* __restrict__ input, const float* __restrict__ filter,
-                  float* __restrict__ grad_input, float* __restrict__ gw_partial, int* __restrict__ counters)
+                  float* __restrict__ grad_input, float* __restrict__ gw_partial)
 {
     static_assert(VEC % R == 0, "a lane's flat strip must cover whole input channels");
     constexpr int VI = VEC / R;                          // input channels per lane
     constexpr int STRIP = 32 * VEC;                      // floats in a warp-wide strip
-    constexpr int NWARPS = T_THREADS / 32;
+    constexpr int NWARPS = THREADS / 32;
     const int Co = C * R;
     extern __shared__ __align__(16) float smem[];
     float* Wsh = smem;                                   // [F][STRIP] flat-channel filter strips of this chunk
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cls = warp % G;                            // my bins: f = s*G + cls, s < SLOTS
     const int cbase = blockIdx.y * STRIP;                // first flat channel of this chunk
-    for (int t = threadIdx.x; t < F * STRIP; t += T_THREADS) {
+    for (int t = threadIdx.x; t < F * STRIP; t += THREADS) {
         const int f = t / STRIP, ch = cbase + t % STRIP;
         Wsh[t] = (ch < Co) ? __ldg(filter + (size_t)f * Co + ch) : 0.f;
     }
@@ -306,86 +305,58 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp
     const int i0 = cbase + lane * VEC;                   // my first flat channel
     const bool active = i0 < Co;
     const int i0ld = active ? i0 : 0;                    // idle lanes load a valid strip, never store
-    const int cin0 = i0ld / R;                           // my first input channel
     const unsigned gsStrideB = (unsigned)Co * 4u;
-    const unsigned zoff = (Mp - 1u) * gsStrideB;         // the zero row of every cloud
-    const size_t gcloudB = (size_t)Mp * Co * 4;
+    const unsigned zoff = zrow * gsStrideB;              // padding edges gather the zero row
+    const char* gb = reinterpret_cast<const char*>(gs) + (size_t)i0ld * 4;
+    const float* inl = input + i0ld / R;                 // my first input channel
+    float* gil = grad_input + i0ld / R;
     const float* wlane = Wsh + (size_t)cls * STRIP + lane * VEC;      // strip of my first bin; next bin: + G*STRIP
     const int wstep = G * STRIP;
-    const int FP = G * SLOTS;
-    const unsigned nchunks = (rows + rpc - 1) / rpc;
-    int* ctr = counters + blockIdx.y * G + cls;
+    const unsigned FP = (unsigned)(G * SLOTS);
+    const unsigned W = gridDim.x * (NWARPS / G);         // warps of my class in the grid
+    const unsigned segoff = (unsigned)(cls * SLOTS);
 
-    // ---- chunk iterator (runs two points ahead of the gathers) ----
-    unsigned it_row = 0, it_rend = 0, it_b = 0, it_n = 0;
-    bool it_valid = true;
-    int it_next = 0;                                     // lane 0: id of the chunk after the current one
-    auto fetch = [&]() { int c = 0; if (lane == 0) c = atomicAdd(ctr, 1); return c; };
-    auto open_chunk = [&](unsigned c) {
-        if (c >= nchunks) { it_valid = false; return; }
-        it_row = c * rpc; it_rend = min(it_row + rpc, rows);
-        it_b = it_row / N; it_n = it_row - it_b * N;
+    // stage "boundaries": lane 0 loads the start, lane 1 the end of my sub-list of point `row`
+    auto load_b = [&](unsigned row) {
+        int bv = 0;
+        if (row < rows) {
+            const unsigned sb = row * FP + segoff;
+            if (lane == 0 && sb > 0) bv = __ldg(seg + sb - 1);
+            if (lane == 1) bv = __ldg(seg + sb + SLOTS - 1);
+        }
+        return bv;
     };
-    {
-        const unsigned c = (unsigned)__shfl_sync(FULL_MASK, fetch(), 0);
-        it_next = fetch();
-        open_chunk(c);
-    }
-    auto advance = [&]() {
-        if (!it_valid) return;
-        it_row++; it_n++;
-        if (it_n == N) { it_n = 0; it_b++; }
-        if (it_row >= it_rend) {
-            const unsigned c = (unsigned)__shfl_sync(FULL_MASK, it_next, 0);
-            it_next = fetch();
-            open_chunk(c);
+    unsigned row = blockIdx.x * (NWARPS / G) + warp / G;
+    // point i+1: boundaries resolved, entries + input strip in flight; point i+2: boundaries in flight
+    int bv2 = load_b(row);
+    int beg1, end1; unsigned e0_1 = 0, e1_1 = 0; float in1[VI];
+    auto stage_e = [&](unsigned r1, int bv) {
+        beg1 = __shfl_sync(FULL_MASK, bv, 0); end1 = __shfl_sync(FULL_MASK, bv, 1);
+        e0_1 = 0; e1_1 = 0;
+        if (end1 > beg1) {
+            if (beg1 + lane < end1) e0_1 = __ldg(entries + beg1 + lane);
+            if (beg1 + 32 + lane < end1) e1_1 = __ldg(entries + beg1 + 32 + lane);
+            VecIO<VI>::ld(in1, inl + (size_t)r1 * C, true);
         }
     };
-
-    // stage "boundaries": lane 0 holds the start, lane 1 the end of my sub-list of point `row`
-    struct StageB { unsigned row, b; bool valid; int bv; };
-    auto make_b = [&]() {
-        StageB x; x.row = it_row; x.b = it_b; x.valid = it_valid; x.bv = 0;
-        if (it_valid) {
-            const size_t sb = (size_t)it_row * FP + (size_t)cls * SLOTS;
-            if (lane == 0 && sb > 0) x.bv = __ldg(seg + sb - 1);
-            if (lane == 1) x.bv = __ldg(seg + sb + SLOTS - 1);
-        }
-        return x;
-    };
-    // stage "entries": first 64 entries of the sub-list and the point's input strip
-    struct StageE { unsigned row, b; bool valid; int beg, end; unsigned e0, e1; float in[VI]; };
-    auto make_e = [&](const StageB& x) {
-        StageE y; y.row = x.row; y.b = x.b; y.valid = x.valid;
-        y.beg = __shfl_sync(FULL_MASK, x.bv, 0); y.end = __shfl_sync(FULL_MASK, x.bv, 1);
-        y.e0 = 0; y.e1 = 0;
 #pragma unroll
-        for (int v = 0; v < VI; v++) y.in[v] = 0.f;
-        if (x.valid && y.end > y.beg) {
-            if (y.beg + lane < y.end) y.e0 = __ldg(entries + y.beg + lane);
-            if (y.beg + 32 + lane < y.end) y.e1 = __ldg(entries + y.beg + 32 + lane);
-            VecIO<VI>::ld(y.in, input + (size_t)x.row * C + cin0, true);
-        }
-        return y;
-    };
+    for (int v = 0; v < VI; v++) in1[v] = 0.f;
+    stage_e(row, bv2);
+    bv2 = load_b(row + W);
 
-    StageB sB = make_b(); advance();
-    StageE sE = make_e(sB);
-    sB = make_b(); advance();
-
-    while (sE.valid) {
-        const StageE cur = sE;
-        sE = make_e(sB);                                  // loads for point i+1 (boundaries arrived during point i-1)
-        sB = make_b(); advance();                         // boundary loads for point i+2
-        if (cur.end <= cur.beg) continue;
-
+    for (; row < rows; row += W) {
+        const int beg = beg1, end = end1;
+        const unsigned ce0 = e0_1, ce1 = e1_1;
         float inx[VEC];                                   // in[b,n,c] expanded to my flat channels
 #pragma unroll
-        for (int e = 0; e < VEC; e++) inx[e] = cur.in[e / R];
+        for (int e = 0; e < VEC; e++) inx[e] = in1[e / R];
+        stage_e(row + W, bv2);                            // loads for point i+1 (its boundaries arrived during point i-1)
+        bv2 = load_b(row + 2 * W);                        // boundary loads for point i+2
+        if (end <= beg) continue;
+
         float gi[VEC], T[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; e++) { gi[e] = 0.f; T[e] = 0.f; }
-        const char* gb = reinterpret_cast<const char*>(gs) + cur.b * gcloudB + (size_t)i0ld * 4;
 
         auto consume = [&](const float (&v)[VEC], int code) {
             strip_add<VEC>(T, v);
@@ -408,15 +379,23 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp
         };
         auto consume4 = [&](int p, const float (&v)[4][VEC]) {
             const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
-            consume(v[0], cc.x); consume(v[1], cc.y); consume(v[2], cc.z); consume(v[3], cc.w);
+            if (((cc.x | cc.y | cc.z | cc.w) & 1) == 0) {  // no segment ends inside this batch (the common case)
+                float u[VEC], w2[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; e++) { u[e] = v[0][e]; w2[e] = v[2][e]; }
+                strip_add<VEC>(u, v[1]); strip_add<VEC>(w2, v[3]);
+                strip_add<VEC>(T, u); strip_add<VEC>(T, w2);
+            } else {
+                consume(v[0], cc.x); consume(v[1], cc.y); consume(v[2], cc.z); consume(v[3], cc.w);
+            }
         };
 
-        for (int kt = cur.beg; kt < cur.end; kt += 64) {
-            const int nt = min(64, cur.end - kt);
+        for (int kt = beg; kt < end; kt += 64) {
+            const int nt = min(64, end - kt);
             const int nt4 = (nt + 3) & ~3;
             const int p0 = lane, p1 = 32 + lane;
-            unsigned e0 = cur.e0, e1 = cur.e1;
-            if (kt != cur.beg) {                           // only the first tile was prefetched
+            unsigned e0 = ce0, e1 = ce1;
+            if (kt != beg) {                               // only the first tile was prefetched
                 e0 = 0; e1 = 0;
                 if (p0 < nt) e0 = __ldg(entries + kt + p0);
                 if (p1 < nt) e1 = __ldg(entries + kt + p1);
@@ -426,28 +405,34 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp
             const int nx1 = __shfl_down_sync(FULL_MASK, s1, 1);
             const int first1 = __shfl_sync(FULL_MASK, s1, 0);
             if (lane == 31) nx0 = first1;
-            if (p0 < nt) {
-                sOff[p0] = (e0 >> 8) * gsStrideB;
-                sCode[p0] = (s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0);
-            } else if (p0 < nt4) {
-                sOff[p0] = zoff; sCode[p0] = 0;
+            if (p0 < nt4) {
+                const bool real = p0 < nt;
+                sOff[p0] = real ? (e0 >> 8) * gsStrideB : zoff;
+                sCode[p0] = real ? ((s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0)) : 0;
             }
-            if (p1 < nt) {
-                sOff[p1] = (e1 >> 8) * gsStrideB;
-                sCode[p1] = (s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0);
-            } else if (p1 < nt4) {
-                sOff[p1] = zoff; sCode[p1] = 0;
+            if (p1 < nt4) {
+                const bool real = p1 < nt;
+                sOff[p1] = real ? (e1 >> 8) * gsStrideB : zoff;
+                sCode[p1] = real ? ((s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0)) : 0;
             }
             __syncwarp();
-            float va[4][VEC], vb[4][VEC];
-            load4(0, va);
-            for (int p = 0; p < nt4; p += 8) {               // eight independent gathers in flight
-                const bool more = p + 4 < nt4;
-                if (more) load4(p + 4, vb);
-                consume4(p, va);
-                if (more) {
-                    if (p + 8 < nt4) load4(p + 8, va);
-                    consume4(p + 4, vb);
+            if constexpr (DEPTH == 2) {                        // eight independent gathers in flight
+                float va[4][VEC], vb[4][VEC];
+                load4(0, va);
+                for (int p = 0; p < nt4; p += 8) {
+                    const bool more = p + 4 < nt4;
+                    if (more) load4(p + 4, vb);
+                    consume4(p, va);
+                    if (more) {
+                        if (p + 8 < nt4) load4(p + 8, va);
+                        consume4(p + 4, vb);
+                    }
+                }
+            } else {                                           // four in flight
+                for (int p = 0; p < nt4; p += 4) {
+                    float va[4][VEC];
+                    load4(p, va);
+                    consume4(p, va);
                 }
             }
             __syncwarp();                                      // sOff/sCode are rewritten by the next tile/point
@@ -461,7 +446,7 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp
                 for (int j = 0; j < R; j++) t += gi[v * R + j];
                 o[v] = t;
             }
-            VecIO<VI>::red(grad_input + (size_t)cur.row * C + cin0, o);
+            VecIO<VI>::red(gil + (size_t)row * C, o);
         }
     }
     // partial [blockIdx.x][warp / G][f][flat channel]: every (f, channel) of a partial is written by exactly one warp
@@ -481,33 +466,33 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned rpc, unsigned N, unsigned Mp
 
 // ------------------------------------------------------------------------------------ host helpers
 struct TPlanMain {
-    int vec, chunks, grid_x, threads, ngroups;
+    int vec, chunks, grid_x, threads, per_cta;     // per_cta: filter partials one CTA writes (warps / G)
     size_t smem;
-    unsigned rpc;
 };
 
 static bool t_plan_main(int B, int N, int M, int F, int C, int r, const TGeom& g, TPlanMain* out)
 {
     if (!g.ok || (r != 1 && r != 2)) return false;
     const long long Co = (long long)C * r;
-    if ((long long)(M + 1) * Co * 4 >= (1LL << 32)) return false;       // 32-bit byte offsets inside a cloud of gs
+    if (((long long)B * M + 1) * Co * 4 >= (1LL << 32)) return false;     // 32-bit byte offsets into gs
     int vec = pick_vec_full_warp((int)Co);
     if (vec % r != 0) vec = r;                                            // a lane's strip covers whole input channels (Co % r == 0)
     TPlanMain p{};
     p.vec = vec;
     p.chunks = (int)((Co + 32 * vec - 1) / (32 * vec));
-    p.threads = T_THREADS;
-    if (T_WARPS % g.G) return false;
-    p.ngroups = T_WARPS / g.G;
-    p.smem = ((size_t)F + (size_t)T_WARPS * g.SLOTS) * 32 * vec * sizeof(float) + (size_t)T_WARPS * 128 * sizeof(int);
+    const int nw = t_warps();
+    p.threads = nw * 32;
+    if (nw % g.G) return false;
+    p.per_cta = nw / g.G;
+    p.smem = ((size_t)F + (size_t)nw * g.SLOTS) * 32 * vec * sizeof(float) + (size_t)nw * 128 * sizeof(int);
     if (p.smem > SMEM_CAP) return false;
     const long long rows = (long long)B * N;
-    p.rpc = (unsigned)tune_int("SPH3D_BWDT_ROWS_PER_CHUNK", 8);
-    const long long nchunks = (rows + p.rpc - 1) / p.rpc;
     long long want = sm_count();
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
+    const long long need = (rows + p.per_cta - 1) / p.per_cta;             // one point per warp of a class at least
+    if (want > need) want = need;
     if (want < 1) want = 1;
-    p.grid_x = (int)(nchunks < want ? nchunks : want);
+    p.grid_x = (int)want;
     *out = p;
     return true;
 }
@@ -549,17 +534,16 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
 }
 
 // workspace of the gradient call proper (scaled grad_output + filter partials), after an optional plan
-struct TWork { size_t gs_off, part_off, ctr_off, total; size_t P; };
+struct TWork { size_t gs_off, part_off, total; size_t P; };
 
 static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
 {
     TWork w{};
     const size_t Co = (size_t)C * r;
     w.gs_off = 0;
-    w.part_off = align256((size_t)B * (M + 1) * Co * sizeof(float));
-    w.P = (size_t)p.grid_x * p.ngroups;
-    w.ctr_off = w.part_off + align256(w.P * F * Co * sizeof(float));
-    w.total = w.ctr_off + align256((size_t)p.chunks * T_WARPS * sizeof(int));       // chunk counters [channel chunk][class]
+    w.part_off = align256(((size_t)B * M + 1) * Co * sizeof(float));
+    w.P = (size_t)p.grid_x * p.per_cta;
+    w.total = w.part_off + align256(w.P * F * Co * sizeof(float));
     return w;
 }
 
@@ -573,29 +557,32 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     float* part = reinterpret_cast<float*>(work + w.part_off);
     const int* seg = reinterpret_cast<const int*>(plan + g.seg_off);
     const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
-    int* counters = reinterpret_cast<int*>(work + w.ctr_off);
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(counters, 0, (size_t)p.chunks * T_WARPS * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     {
         const int V = (Co % 4 == 0) ? 4 : ((Co % 2 == 0) ? 2 : 1);
-        const size_t total = (size_t)B * (M + 1) * Co / V;
+        const size_t orows = (size_t)B * M;
+        const size_t total = (orows + 1) * Co / V;
         const unsigned gr = grid_for(total, 256, 16);
-        if (V == 4) scale_rows_kernel<4><<<gr, 256, 0, st>>>(total, (unsigned)M, (unsigned)(Co / 4), K, nn_count, grad_output, gs);
-        else if (V == 2) scale_rows_kernel<2><<<gr, 256, 0, st>>>(total, (unsigned)M, (unsigned)(Co / 2), K, nn_count, grad_output, gs);
-        else scale_rows_kernel<1><<<gr, 256, 0, st>>>(total, (unsigned)M, (unsigned)Co, K, nn_count, grad_output, gs);
+        if (V == 4) scale_rows_kernel<4><<<gr, 256, 0, st>>>(total, orows, (unsigned)(Co / 4), K, nn_count, grad_output, gs);
+        else if (V == 2) scale_rows_kernel<2><<<gr, 256, 0, st>>>(total, orows, (unsigned)(Co / 2), K, nn_count, grad_output, gs);
+        else scale_rows_kernel<1><<<gr, 256, 0, st>>>(total, orows, (unsigned)Co, K, nn_count, grad_output, gs);
         SPH3D_CHECK_LAUNCH();
     }
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * N);
+    const unsigned zrow = (unsigned)((long long)B * M);
+#define LAUNCH_T2(V, RR, TH, DP)                                                                                 \
+    do {                                                                                                         \
+        e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP>, p.smem);                                                  \
+        if (e != cudaSuccess) return (int)e;                                                                     \
+        conv_bwd_t_kernel<V, RR, TH, DP><<<grid, TH, p.smem, st>>>(rows, zrow, F, C, g.G, g.SLOTS, seg, ent, gs, \
+                                                                   input, filter, grad_input, part);             \
+    } while (0)
 #define LAUNCH_T(V, RR)                                                                                          \
     do {                                                                                                         \
-        e = set_smem(conv_bwd_t_kernel<V, RR>, p.smem);                                                          \
-        if (e != cudaSuccess) return (int)e;                                                                     \
-        conv_bwd_t_kernel<V, RR><<<grid, T_THREADS, p.smem, st>>>(rows, p.rpc, (unsigned)N, (unsigned)(M + 1), F, C, g.G, \
-                                                                  g.SLOTS, seg, ent, gs, input, filter, grad_input, part, \
-                                                                  counters);                                    \
+        if (p.threads == 1024) LAUNCH_T2(V, RR, 1024, 1);                                                        \
+        else LAUNCH_T2(V, RR, 768, 2);                                                                           \
     } while (0)
     if (p.vec == 4 && r == 1) LAUNCH_T(4, 1);
     else if (p.vec == 4 && r == 2) LAUNCH_T(4, 2);
@@ -603,6 +590,7 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     else if (p.vec == 2 && r == 2) LAUNCH_T(2, 2);
     else if (p.vec == 1 && r == 1) LAUNCH_T(1, 1);
     else return (int)cudaErrorInvalidValue;
+#undef LAUNCH_T2
 #undef LAUNCH_T
     SPH3D_CHECK_LAUNCH();
     int rc = launch_reduce_partials((int)w.P, (size_t)F * Co, part, grad_filter, st);

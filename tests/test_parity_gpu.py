@@ -224,7 +224,7 @@ def _plan_layout(B, N, M, F, K):
     """layout of the sph3d_conv_transpose plan (csrc/conv_bwd_t.cu, t_geom): int32 words"""
     for G in (1, 2, 3, 4, 6, 8, 12, 24):
         SL = -(-F // G)
-        if SL <= 255 and 24 * SL * 512 + F * 512 + 24 * 512 <= 200 * 1024:
+        if SL <= 127 and 24 * SL * 512 + F * 512 + 24 * 512 <= 210 * 1024:
             break
     FP = SL * G
     nseg = B * N * FP
@@ -258,7 +258,7 @@ def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
     n, f = idx[b, m, k].astype(np.int64), filt[b, m, k].astype(np.int64)
     key = (b * N + n) * FP + (f % G) * SL + f // G
     order = np.lexsort((m, key))
-    want_entries = ((m[order].astype(np.int64) << 8) | (f[order] // G)).astype(np.uint32)
+    want_entries = (((b[order] * M + m[order]).astype(np.int64) << 8) | (f[order] // G)).astype(np.uint32)
     counts = np.bincount(key, minlength=nseg)
     assert_equal(seg_end, np.cumsum(counts), case[0] + " segment ends")
     got = plan[ent_w:ent_w + len(want_entries)].view(np.uint32)
@@ -271,7 +271,7 @@ def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
 @pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
 def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch):
     """the split form (plan built once, reused) equals the one-call form; with canonical segment order
-    (SPH3D_BWDT_SORT=1) bit for bit in grad_filter"""
+    (SPH3D_BWDT_SORT=1; the point-to-warp assignment is static) bit for bit in grad_filter"""
     monkeypatch.setenv("SPH3D_BWDT_SORT", "1")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
@@ -281,8 +281,21 @@ def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch):
         gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad_planned(T(x), T(W), T(go), T(cnt), plan, idx.shape[2])
         assert_close(A(gi), ti, 1e-5, case[0] + " planned grad_input")
         assert_close(A(gf), tf, 1e-5, case[0] + " planned grad_filter")
+    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
     gi1, gf1 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
     assert_equal(A(gf), A(gf1), case[0] + " planned vs one-call grad_filter")
+
+
+@pytest.mark.parametrize("case", TRANSPOSE_CASES[:4], ids=[c[0] for c in TRANSPOSE_CASES[:4]])
+def test_transposed_backward_32_warp_configuration(case, pkg, oracle, monkeypatch):
+    """SPH3D_BWDT_THREADS=1024: 32 warps per CTA, 4 gathers in flight, bin classes dividing 32"""
+    monkeypatch.setenv("SPH3D_BWDT_THREADS", "1024")
+    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
+    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
+    go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
+    ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
+    gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_close(A(gi), ti, 1e-5, case[0] + " grad_input"); assert_close(A(gf), tf, 1e-5, case[0] + " grad_filter")
 
 
 @pytest.mark.parametrize("case", CONV_CASES[:6], ids=[c[0] for c in CONV_CASES[:6]])
@@ -303,6 +316,7 @@ def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch
 @pytest.mark.parametrize("case", TRANSPOSE_CASES[:3], ids=[c[0] for c in TRANSPOSE_CASES[:3]])
 def test_transposed_backward_canonical_order_is_deterministic(case, pkg, oracle, monkeypatch):
     monkeypatch.setenv("SPH3D_BWDT_SORT", "1")
+    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(66, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
     gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
