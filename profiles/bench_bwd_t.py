@@ -78,11 +78,16 @@ def main():
     res["planned_ms"] = timeit(planned, args.iters)
     if args.sweep:
         sw = {}
-        for name, kw in (("768thr_g4", dict(SPH3D_BWDT_G=4)), ("1024thr", dict(SPH3D_BWDT_THREADS=1024)),
-                         ("1024thr_g8", dict(SPH3D_BWDT_THREADS=1024, SPH3D_BWDT_G=8))):
+        cfgs = [("768_static", {}), ("1024_static", dict(SPH3D_BWDT_THREADS=1024)),
+                ("768_g8", dict(SPH3D_BWDT_G=8)), ("768_g2", dict(SPH3D_BWDT_G=2))]
+        for th in (768, 1024):
+            for rpc in (1, 2, 4):
+                cfgs.append(("%d_dyn_rpc%d" % (th, rpc), dict(SPH3D_BWDT_THREADS=th, SPH3D_BWDT_DYNAMIC=1, SPH3D_BWDT_ROWS_PER_CHUNK=rpc)))
+        for name, kw in cfgs:
             env(**kw)
             plan2 = build()                                   # the plan geometry follows the launch configuration
-            sw[name] = timeit(lambda: C3.depthwise_conv3d_grad_planned(d["x"], d["W"], d["go"], d["cnt"], plan2, K), args.iters)
+            if plan2 is not None:
+                sw[name] = timeit(lambda: C3.depthwise_conv3d_grad_planned(d["x"], d["W"], d["go"], d["cnt"], plan2, K), args.iters)
             env(**{k: None for k in kw})
         res["planned_sweep_ms"] = sw
     print(json.dumps(res))
