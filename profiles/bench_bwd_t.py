@@ -80,9 +80,6 @@ def main():
         sw = {}
         cfgs = [("768_static", {}), ("1024_static", dict(SPH3D_BWDT_THREADS=1024)),
                 ("768_g8", dict(SPH3D_BWDT_G=8)), ("768_g2", dict(SPH3D_BWDT_G=2))]
-        for th in (768, 1024):
-            for rpc in (1, 2, 4):
-                cfgs.append(("%d_dyn_rpc%d" % (th, rpc), dict(SPH3D_BWDT_THREADS=th, SPH3D_BWDT_DYNAMIC=1, SPH3D_BWDT_ROWS_PER_CHUNK=rpc)))
         for name, kw in cfgs:
             env(**kw)
             plan2 = build()                                   # the plan geometry follows the launch configuration

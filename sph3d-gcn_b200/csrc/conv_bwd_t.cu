@@ -274,17 +274,12 @@ __device__ __forceinline__ void st_strip_smem(float* p, const float (&v)[VEC])
 // cloud together (the gathered cloud stays L2-resident), and the assignment is reproducible.
 // Per point the warp runs a three-stage software pipeline, two points ahead: segment boundaries (i+2), entry
 // list + input strip (i+1), gathers (i); inside a point 4*DEPTH feature-strip gathers are in flight.
-// keeps a loop-invariant address in a register: without it ptxas rebuilds these from %tid / %ctaid inside the hot loop
-// (11 instructions per batch of four gathers) to stay under the register cap
-template <typename P>
-__device__ __forceinline__ void pin(P*& p) { asm volatile("" : "+l"(p)); }
-
-template <int VEC, int R, int THREADS, int DEPTH, bool DYN>
+template <int VEC, int R, int THREADS, int DEPTH>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of gs */, int F, int C, int G, int SLOTS,
                   const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
                   const float* __restrict__ input, const float* __restrict__ filter,
-                  float* __restrict__ grad_input, float* __restrict__ gw_partial, int* __restrict__ counters, unsigned rpc)
+                  float* __restrict__ grad_input, float* __restrict__ gw_partial)
 {
     static_assert(VEC % R == 0, "a lane's flat strip must cover whole input channels");
     constexpr int VI = VEC / R;                          // input channels per lane
@@ -324,28 +319,6 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
     const unsigned FP = (unsigned)(G * SLOTS);
     const unsigned W = gridDim.x * (NWARPS / G);         // warps of my class in the grid
     const unsigned segoff = (unsigned)(cls * SLOTS);
-    pin(gb); pin(inl); pin(gil); pin(wlane); pin(accS); pin(sOff); pin(sCode);
-
-    // DYN: the class's warps pull chunks of `rpc` consecutive points from a global counter instead of striding
-    unsigned it = 0, it_end = 0;
-    int nxt = 0;                                         // lane 0: the chunk after the current one (already fetched)
-    bool it_done = false;
-    int* ctr = counters + blockIdx.y * G + cls;
-    const unsigned nchunks = DYN ? (rows + rpc - 1) / rpc : 0;
-    auto fetch = [&]() { int c = 0; if (lane == 0) c = atomicAdd(ctr, 1); return c; };
-    auto next_row = [&](unsigned prev) -> unsigned {
-        if constexpr (!DYN) {
-            return prev + W;
-        } else {
-            if (it < it_end) return it++;
-            if (it_done) return rows;
-            const unsigned c = (unsigned)__shfl_sync(FULL_MASK, nxt, 0);
-            if (c >= nchunks) { it_done = true; return rows; }
-            nxt = fetch();
-            it = c * rpc; it_end = min(it + rpc, rows);
-            return it++;
-        }
-    };
 
     // stage "boundaries": lane 0 loads the start, lane 1 the end of my sub-list of point `row`
     auto load_b = [&](unsigned row) {
@@ -357,14 +330,8 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
         }
         return bv;
     };
-    unsigned row;
-    if constexpr (DYN) {
-        nxt = fetch();
-        row = next_row(0);
-    } else {
-        row = blockIdx.x * (NWARPS / G) + warp / G;
-    }
-    unsigned row1 = next_row(row);
+    unsigned row = blockIdx.x * (NWARPS / G) + warp / G;
+    unsigned row1 = row + W;
     // point i+1: boundaries resolved, entries + input strip in flight; point i+2: boundaries in flight
     int bv2 = load_b(row);
     int beg1, end1; unsigned e0_1 = 0, e1_1 = 0; float in1[VI];
@@ -391,7 +358,7 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
         for (int e = 0; e < VEC; e++) inx[e] = in1[e / R];
         stage_e(row1, bv2);                               // loads for point i+1 (its boundaries arrived during point i-1)
         row = row1;
-        row1 = next_row(row1);
+        row1 += W;
         bv2 = load_b(row1);                               // boundary loads for point i+2
         if (end <= beg) continue;
 
@@ -575,7 +542,7 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
 }
 
 // workspace of the gradient call proper (scaled grad_output + filter partials), after an optional plan
-struct TWork { size_t gs_off, part_off, ctr_off, total; size_t P; };
+struct TWork { size_t gs_off, part_off, total; size_t P; };
 
 static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
 {
@@ -584,8 +551,7 @@ static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
     w.gs_off = 0;
     w.part_off = align256(((size_t)B * M + 1) * Co * sizeof(float));
     w.P = (size_t)p.grid_x * p.per_cta;
-    w.ctr_off = w.part_off + align256(w.P * F * Co * sizeof(float));
-    w.total = w.ctr_off + align256((size_t)p.chunks * 32 * sizeof(int));            // chunk counters [channel chunk][class]
+    w.total = w.part_off + align256(w.P * F * Co * sizeof(float));
     return w;
 }
 
@@ -599,15 +565,8 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     float* part = reinterpret_cast<float*>(work + w.part_off);
     const int* seg = reinterpret_cast<const int*>(plan + g.seg_off);
     const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
-    int* counters = reinterpret_cast<int*>(work + w.ctr_off);
-    const int dyn = tune_int("SPH3D_BWDT_DYNAMIC", 0);
-    const unsigned rpc = (unsigned)tune_int("SPH3D_BWDT_ROWS_PER_CHUNK", 2);
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
     if (e != cudaSuccess) return (int)e;
-    if (dyn) {
-        e = cudaMemsetAsync(counters, 0, (size_t)p.chunks * 32 * sizeof(int), st);
-        if (e != cudaSuccess) return (int)e;
-    }
     {
         const int V = (Co % 4 == 0) ? 4 : ((Co % 2 == 0) ? 2 : 1);
         const size_t orows = (size_t)B * M;
@@ -621,17 +580,12 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * N);
     const unsigned zrow = (unsigned)((long long)B * M);
-#define LAUNCH_T3(V, RR, TH, DP, DY)                                                                             \
-    do {                                                                                                         \
-        e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP, DY>, p.smem);                                              \
-        if (e != cudaSuccess) return (int)e;                                                                     \
-        conv_bwd_t_kernel<V, RR, TH, DP, DY><<<grid, TH, p.smem, st>>>(rows, zrow, F, C, g.G, g.SLOTS, seg, ent, gs, \
-                                                                       input, filter, grad_input, part, counters, rpc); \
-    } while (0)
 #define LAUNCH_T2(V, RR, TH, DP)                                                                                 \
     do {                                                                                                         \
-        if (dyn) LAUNCH_T3(V, RR, TH, DP, true);                                                                 \
-        else LAUNCH_T3(V, RR, TH, DP, false);                                                                    \
+        e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP>, p.smem);                                                  \
+        if (e != cudaSuccess) return (int)e;                                                                     \
+        conv_bwd_t_kernel<V, RR, TH, DP><<<grid, TH, p.smem, st>>>(rows, zrow, F, C, g.G, g.SLOTS, seg, ent, gs, \
+                                                                   input, filter, grad_input, part);             \
     } while (0)
 #define LAUNCH_T(V, RR)                                                                                          \
     do {                                                                                                         \
@@ -645,7 +599,6 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     else if (p.vec == 1 && r == 1) LAUNCH_T(1, 1);
     else return (int)cudaErrorInvalidValue;
 #undef LAUNCH_T2
-#undef LAUNCH_T3
 #undef LAUNCH_T
     SPH3D_CHECK_LAUNCH();
     int rc = launch_reduce_partials((int)w.P, (size_t)F * Co, part, grad_filter, st);

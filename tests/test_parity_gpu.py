@@ -287,13 +287,9 @@ def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("case", TRANSPOSE_CASES[:4], ids=[c[0] for c in TRANSPOSE_CASES[:4]])
-@pytest.mark.parametrize("dynamic", [0, 1])
-def test_transposed_backward_32_warp_configuration(case, dynamic, pkg, oracle, monkeypatch):
-    """SPH3D_BWDT_THREADS=1024: 32 warps per CTA, 4 gathers in flight, bin classes dividing 32;
-    SPH3D_BWDT_DYNAMIC=1: points handed out by a global counter instead of round-robin"""
+def test_transposed_backward_32_warp_configuration(case, pkg, oracle, monkeypatch):
+    """SPH3D_BWDT_THREADS=1024: 32 warps per CTA, 4 gathers in flight, bin classes dividing 32"""
     monkeypatch.setenv("SPH3D_BWDT_THREADS", "1024")
-    monkeypatch.setenv("SPH3D_BWDT_DYNAMIC", str(dynamic))
-    monkeypatch.setenv("SPH3D_BWDT_ROWS_PER_CHUNK", "3")
     monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
@@ -315,17 +311,6 @@ def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch
     assert_close(A(gf), tf, 1e-5, case[0] + " row-owned grad_filter")
     gi2, gf2 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
     assert_equal(A(gf2), A(gf), "row-owned grad_filter determinism")
-
-
-@pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
-def test_transposed_backward_dynamic_schedule(case, pkg, oracle, monkeypatch):
-    monkeypatch.setenv("SPH3D_BWDT_DYNAMIC", "1")
-    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
-    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
-    go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
-    ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
-    gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
-    assert_close(A(gi), ti, 1e-5, case[0] + " grad_input"); assert_close(A(gf), tf, 1e-5, case[0] + " grad_filter")
 
 
 @pytest.mark.parametrize("case", TRANSPOSE_CASES[:3], ids=[c[0] for c in TRANSPOSE_CASES[:3]])
