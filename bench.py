@@ -441,9 +441,29 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         ab_fwd, ab_bwd = algorithmic_bytes(B, N, M, C, r, F, E)
-        dominant = "conv_bwd_kernel" if bwd_ms >= fwd_ms else "conv_fwd_kernel"
-        ab, tms = (ab_bwd, bwd_ms) if dominant == "conv_bwd_kernel" else (ab_fwd, fwd_ms)
+        # the backward op is several launches (graph transposition, scale, conv_bwd_t_kernel, partial reduce): the roofline
+        # line charges the op's algorithmic bytes against the time of ALL of them (CUDA events around the op)
+        dominant = "conv_bwd_op" if bwd_ms >= fwd_ms else "conv_fwd_kernel"
+        ab, tms = (ab_bwd, bwd_ms) if dominant == "conv_bwd_op" else (ab_fwd, fwd_ms)
         ach = ab / (tms * 1e-3) / 1e9
+        # split of the backward op, measured through the planned entry points (same kernels, plan built once)
+        C3 = S.tf_conv3d
+        def _t(fn, n=10):
+            fn(); torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b_.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n
+        split = {}
+        try:
+            plan = C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N)
+            if plan is not None:
+                split["conv_transpose_ms"] = _t(lambda: C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N))
+                split["conv_bwd_planned_ms"] = _t(lambda: C3.depthwise_conv3d_grad_planned(d["x"], d["W"], d["go"], d["cnt"], plan, K))
+        except Exception as e:
+            split["planned_error"] = repr(e)
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -463,7 +483,8 @@ def main():
             "kernels": {"conv_fwd_ms": fwd_ms, "conv_bwd_ms": bwd_ms,
                         "conv_fwd_gbs": ab_fwd / (fwd_ms * 1e-3) / 1e9, "conv_bwd_gbs": ab_bwd / (bwd_ms * 1e-3) / 1e9,
                         "conv_fwd_frac": ab_fwd / (fwd_ms * 1e-3) / 1e9 / peak, "conv_bwd_frac": ab_bwd / (bwd_ms * 1e-3) / 1e9 / peak,
-                        "logical_gather_gbs_fwd": (4.0 * E * C + 4.0 * B * M * C * r + 8.0 * E) / (fwd_ms * 1e-3) / 1e9},
+                        "logical_gather_gbs_fwd": (4.0 * E * C + 4.0 * B * M * C * r + 8.0 * E) / (fwd_ms * 1e-3) / 1e9,
+                        "logical_gather_gbs_bwd": (4.0 * E * C * r + 8.0 * B * N * C + 4.0 * E) / (bwd_ms * 1e-3) / 1e9, **split},
         }
         if world == 1 and not args.no_extras:
             try:

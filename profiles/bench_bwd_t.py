@@ -78,8 +78,9 @@ def main():
     res["planned_ms"] = timeit(planned, args.iters)
     if args.sweep:
         sw = {}
-        cfgs = [("768_static", {}), ("1024_static", dict(SPH3D_BWDT_THREADS=1024)),
-                ("768_g8", dict(SPH3D_BWDT_G=8)), ("768_g2", dict(SPH3D_BWDT_G=2))]
+        cfgs = [("768x2", {}), ("1024x1", dict(SPH3D_BWDT_THREADS=1024)), ("640x2", dict(SPH3D_BWDT_THREADS=640)),
+                ("640x3", dict(SPH3D_BWDT_THREADS=640, SPH3D_BWDT_DEPTH=3)), ("512x3", dict(SPH3D_BWDT_THREADS=512)),
+                ("512x4", dict(SPH3D_BWDT_THREADS=512, SPH3D_BWDT_DEPTH=4)), ("768x2_g2", dict(SPH3D_BWDT_G=2))]
         for name, kw in cfgs:
             env(**kw)
             plan2 = build()                                   # the plan geometry follows the launch configuration

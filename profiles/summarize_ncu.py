@@ -68,6 +68,23 @@ def main():
                 "kernel": name, "report": os.path.basename(rep), "tag": tag}
         except Exception as e:                                                   # keep the markdown even if a unit is new
             out.append("(summary json skipped: %r)\n" % (e,))
+    # the backward op is several launches: aggregate them per op (bench.py roofline.traffic for "conv_bwd_op")
+    BWD = ("transpose_edges_kernel", "scan_reduce_kernel", "scan_apply_kernel", "sort_segments_kernel", "scale_rows_kernel",
+           "conv_bwd_t_kernel", "reduce_partials_kernel")
+    ops = sum(1 for d in data if short(d[col["Kernel Name"]]).split("<")[0] == "conv_bwd_t_kernel")
+    if ops:
+        tot_b, tot_ms, n = 0.0, 0.0, 0
+        for d in data:
+            if short(d[col["Kernel Name"]]).split("<")[0] in BWD:
+                ub = lambda m: float(d[col[m]]) * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(units[col[m]].lower(), 1)
+                tot_b += ub("dram__bytes_read.sum") + ub("dram__bytes_write.sum")
+                tot_ms += float(d[col["gpu__time_duration.sum"]]) * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(
+                    units[col["gpu__time_duration.sum"]].lower().replace("msecond", "ms").replace("usecond", "us").replace("nsecond", "ns").replace("second", "s"), 1)
+                n += 1
+        summary["kernels"]["conv_bwd_op"] = {"dram_bytes_per_launch": tot_b / ops, "duration_ms_under_ncu": tot_ms / ops,
+                                             "kernel": "all %d kernels of one sph3d_depthwise_conv3d_grad call (transposed form)" % (n // ops),
+                                             "report": os.path.basename(rep), "tag": tag}
+        out.append("## conv backward op (sum over its %d kernels)\n\nDRAM bytes %.1f MB, device time %.3f ms (under ncu)\n" % (n // ops, tot_b / ops / 1e6, tot_ms / ops))
     open(os.path.join(here, "%s_ncu.md" % tag), "w").write("\n".join(out) + "\n")
     json.dump(summary, open(summary_path, "w"), indent=1, sort_keys=True)
     print("wrote", os.path.join(here, "%s_ncu.md" % tag), "and", summary_path)

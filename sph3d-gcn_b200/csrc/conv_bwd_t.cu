@@ -15,9 +15,9 @@
 // reduction pass.
 //
 // Pipeline of one call (all on the caller's stream, caller-owned workspace):
-//   1. transpose_count : seg[(b,n), f'] += 1 per edge (integer RED), f' = (f % G)*SLOTS + f / G
-//   2. exclusive scan of seg (two small kernels), 3. transpose_fill: entries[pos] = (m << 8) | (f / G)
-//      with pos from an integer atomic cursor; afterwards seg[s] is the END of segment s
+//   1. transpose_edges<count>: rank = seg[(b,n), f']++ per edge (one returning integer atomic), f' = (f % G)*SLOTS + f / G
+//   2. exclusive scan of seg (two small kernels): seg[s] = START of segment s, seg[B*N*G*SLOTS] = number of edges
+//   3. transpose_edges<fill>: entries[seg[s] + rank] = (b*M+m) << 8 | (f / G), no atomics
 //   4. (optional, default on) per-segment insertion sort of the entries by m => run-to-run deterministic
 //   5. scale_rows: gs[b,m,:] = gO[b,m,:] / cnt[b,m] into a (B, M+1, C*r) buffer whose row M is zero
 //      (the landing row of the padding edges that round every tile up to a multiple of four)
@@ -40,17 +40,30 @@
 
 namespace sph3d {
 
-// warps per CTA of the gather kernel: 24 (768 threads, 80 registers, 8 gathers in flight per warp; default) or
-// 32 (SPH3D_BWDT_THREADS=1024: 64 registers, 4 in flight)
-static inline int t_warps() { return tune_int("SPH3D_BWDT_THREADS", 768) == 1024 ? 32 : 24; }
+// CTA shape of the gather kernel (one CTA per SM): 768 threads x 8 gathers in flight per warp by default;
+// SPH3D_BWDT_THREADS = 512 / 640 / 1024 and SPH3D_BWDT_DEPTH select the other compiled shapes (sweeps in profiles/)
+static inline int t_warps()
+{
+    const int t = tune_int("SPH3D_BWDT_THREADS", 768);
+    return (t == 512 || t == 640 || t == 1024) ? t / 32 : 24;
+}
+static inline int t_depth(int warps)
+{
+    const int d = tune_int("SPH3D_BWDT_DEPTH", 0);
+    if (warps == 16) return d == 4 ? 4 : 3;
+    if (warps == 20) return d == 3 ? 3 : 2;
+    if (warps == 32) return 1;
+    return 2;
+}
 constexpr int SCAN_TILE = 4096;          // ints per CTA in the scan kernels (256 threads x 16)
 
 // ------------------------------------------------------------------------------------------- plan
 struct TGeom {
     int G, SLOTS, FP;           // bin classes (f % G), bins per class, G*SLOTS segments per point
-    size_t nseg, nseg_pad;      // B*N*FP, rounded up to SCAN_TILE
+    size_t nseg, nseg_pad;      // B*N*FP; nseg+1 (the total sits behind the last start) rounded up to SCAN_TILE
+    int rank_bytes;             // 2 or 4: width of the per-edge rank scratch
     int scan_blocks;
-    size_t seg_off, sums_off, ent_off, total;   // byte offsets inside the plan
+    size_t seg_off, sums_off, ent_off, rank_off, total;   // byte offsets inside the plan
     bool ok;
 };
 
@@ -82,24 +95,29 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
     if ((long long)B * M * K >= (1LL << 31) || (long long)B * N * G * SL >= (1LL << 31)) return g;
     g.G = G; g.SLOTS = SL; g.FP = G * SL;
     g.nseg = (size_t)B * N * g.FP;
-    g.nseg_pad = (g.nseg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+    g.nseg_pad = (g.nseg + 1 + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
     if (g.nseg_pad / SCAN_TILE > 65536) return g;
     g.scan_blocks = (int)(g.nseg_pad / SCAN_TILE);
     g.seg_off = 0;
     g.sums_off = align256(g.nseg_pad * sizeof(int));
     g.ent_off = g.sums_off + align256((size_t)g.scan_blocks * sizeof(int));
-    g.total = g.ent_off + align256((size_t)B * M * K * sizeof(int));
+    g.rank_bytes = (M <= 65535) ? 2 : 4;                          // a segment holds distinct output points of one cloud
+    g.rank_off = g.ent_off + align256((size_t)B * M * K * sizeof(int));
+    g.total = g.rank_off + align256((size_t)B * M * K * g.rank_bytes);
     g.ok = true;
     return g;
 }
 
 // ------------------------------------------------------------------------------ transpose kernels
-// one thread per edge slot (b,m,k); edges beyond nn_count and malformed ids are skipped
-template <bool FILL>
+// one thread per edge slot (b,m,k); edges beyond nn_count and malformed ids are skipped.
+// Pass 1 (FILL = false): rank of the edge inside its segment from ONE returning integer atomic; seg ends up holding the
+// segment sizes.  Pass 2 (FILL = true, after the exclusive scan): position = start + rank, no atomics.
+template <bool FILL, typename RankT>
 __global__ void __launch_bounds__(256)
 transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G, int SLOTS,
                        const int* __restrict__ nn_index, const int* __restrict__ nn_count,
-                       const int* __restrict__ bin_index, int* __restrict__ seg, unsigned* __restrict__ entries)
+                       const int* __restrict__ bin_index, int* __restrict__ seg, RankT* __restrict__ ranks,
+                       unsigned* __restrict__ entries)
 {
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x) {
         const size_t row = t / (unsigned)K;
@@ -110,10 +128,10 @@ transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G
         const unsigned b = (unsigned)(row / M);
         const size_t s = ((size_t)b * N + n) * (G * SLOTS) + (f % G) * SLOTS + f / G;
         if constexpr (FILL) {
-            const int pos = atomicAdd(seg + s, 1);
+            const int pos = __ldg(seg + s) + (int)ranks[t];
             entries[pos] = ((unsigned)row << 8) | (unsigned)(f / G);     // row = b*M + m: the row of gs this edge gathers
         } else {
-            atomicAdd(seg + s, 1);                                  // result unused: RED.ADD
+            ranks[t] = (RankT)atomicAdd(seg + s, 1);
         }
     }
 }
@@ -189,8 +207,7 @@ __global__ void __launch_bounds__(256)
 sort_segments_kernel(size_t nseg, const int* __restrict__ seg, unsigned* __restrict__ entries)
 {
     for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (size_t)gridDim.x * blockDim.x) {
-        const int end = seg[s];
-        const int beg = s ? seg[s - 1] : 0;
+        const int beg = seg[s], end = seg[s + 1];
         for (int i = beg + 1; i < end; i++) {
             const unsigned x = entries[i];
             int j = i;
@@ -324,9 +341,9 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
     auto load_b = [&](unsigned row) {
         int bv = 0;
         if (row < rows) {
-            const unsigned sb = row * FP + segoff;
-            if (lane == 0 && sb > 0) bv = __ldg(seg + sb - 1);
-            if (lane == 1) bv = __ldg(seg + sb + SLOTS - 1);
+            const unsigned sb = row * FP + segoff;            // seg[s] = start of segment s; seg[nseg] = number of edges
+            if (lane == 0) bv = __ldg(seg + sb);
+            if (lane == 1) bv = __ldg(seg + sb + SLOTS);
         }
         return bv;
     };
@@ -424,23 +441,20 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
                 sCode[p1] = real ? ((s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0)) : 0;
             }
             __syncwarp();
-            if constexpr (DEPTH == 2) {                        // eight independent gathers in flight
-                float va[4][VEC], vb[4][VEC];
-                load4(0, va);
-                for (int p = 0; p < nt4; p += 8) {
-                    const bool more = p + 4 < nt4;
-                    if (more) load4(p + 4, vb);
-                    consume4(p, va);
-                    if (more) {
-                        if (p + 8 < nt4) load4(p + 8, va);
-                        consume4(p + 4, vb);
+            // software pipeline over batches of four gathers, 4*DEPTH strips in flight
+            float v[DEPTH][4][VEC];
+#pragma unroll
+            for (int d = 0; d < DEPTH - 1; d++)
+                if (d * 4 < nt4) load4(d * 4, v[d]);
+            for (int p = 0; p < nt4; p += 4 * DEPTH) {
+#pragma unroll
+                for (int d = 0; d < DEPTH; d++) {
+                    const int pp = p + 4 * d;
+                    if (pp < nt4) {
+                        const int pn = pp + 4 * (DEPTH - 1);
+                        if (pn < nt4) load4(pn, v[(d + DEPTH - 1) % DEPTH]);
+                        consume4(pp, v[d]);
                     }
-                }
-            } else {                                           // four in flight
-                for (int p = 0; p < nt4; p += 4) {
-                    float va[4][VEC];
-                    load4(p, va);
-                    consume4(p, va);
                 }
             }
             __syncwarp();                                      // sOff/sCode are rewritten by the next tile/point
@@ -522,15 +536,18 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
     if (e != cudaSuccess) return (int)e;
     const size_t slots = (size_t)B * M * K;
     const unsigned ge = grid_for(slots, 256, 16);
-    transpose_edges_kernel<false><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, nn_index, nn_count,
-                                                     bin_index, seg, ent);
+    void* ranks = plan + g.rank_off;
+#define EDGES(FILL, RT)                                                                                                    \
+    transpose_edges_kernel<FILL, RT><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, nn_index,       \
+                                                         nn_count, bin_index, seg, reinterpret_cast<RT*>(ranks), ent)
+    if (g.rank_bytes == 2) EDGES(false, unsigned short); else EDGES(false, unsigned);
     SPH3D_CHECK_LAUNCH();
     scan_reduce_kernel<<<g.scan_blocks, 256, 0, st>>>(reinterpret_cast<const int4*>(seg), sums);
     SPH3D_CHECK_LAUNCH();
     scan_apply_kernel<<<g.scan_blocks, 256, 0, st>>>(reinterpret_cast<int4*>(seg), sums);
     SPH3D_CHECK_LAUNCH();
-    transpose_edges_kernel<true><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, nn_index, nn_count,
-                                                    bin_index, seg, ent);
+    if (g.rank_bytes == 2) EDGES(true, unsigned short); else EDGES(true, unsigned);
+#undef EDGES
     SPH3D_CHECK_LAUNCH();
     *launches += 4;
     if (tune_int("SPH3D_BWDT_SORT", 0) == 1) {             // opt-in: canonical order inside every segment
@@ -587,9 +604,14 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
         conv_bwd_t_kernel<V, RR, TH, DP><<<grid, TH, p.smem, st>>>(rows, zrow, F, C, g.G, g.SLOTS, seg, ent, gs, \
                                                                    input, filter, grad_input, part);             \
     } while (0)
+    const int depth = t_depth(p.threads / 32);
 #define LAUNCH_T(V, RR)                                                                                          \
     do {                                                                                                         \
         if (p.threads == 1024) LAUNCH_T2(V, RR, 1024, 1);                                                        \
+        else if (p.threads == 512 && depth == 4) LAUNCH_T2(V, RR, 512, 4);                                       \
+        else if (p.threads == 512) LAUNCH_T2(V, RR, 512, 3);                                                     \
+        else if (p.threads == 640 && depth == 3) LAUNCH_T2(V, RR, 640, 3);                                       \
+        else if (p.threads == 640) LAUNCH_T2(V, RR, 640, 2);                                                     \
         else LAUNCH_T2(V, RR, 768, 2);                                                                           \
     } while (0)
     if (p.vec == 4 && r == 1) LAUNCH_T(4, 1);

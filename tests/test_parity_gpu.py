@@ -228,7 +228,7 @@ def _plan_layout(B, N, M, F, K):
     SL = -(-F // G)
     FP = SL * G
     nseg = B * N * FP
-    nseg_pad = -(-nseg // 4096) * 4096
+    nseg_pad = -(-(nseg + 1) // 4096) * 4096
     a256 = lambda x: (x + 255) // 256 * 256
     sums_off = a256(nseg_pad * 4)
     ent_off = sums_off + a256(nseg_pad // 4096 * 4)
@@ -253,14 +253,14 @@ def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
     assert plan is not None
     plan = A(plan)
     G, SL, FP, nseg, ent_w = _plan_layout(B, N, M, F, K)
-    seg_end = plan[:nseg].astype(np.int64)
+    seg_start = plan[:nseg + 1].astype(np.int64)
     b, m, k = np.nonzero(np.arange(K)[None, None, :] < np.minimum(cnt, K)[:, :, None])
     n, f = idx[b, m, k].astype(np.int64), filt[b, m, k].astype(np.int64)
     key = (b * N + n) * FP + (f % G) * SL + f // G
     order = np.lexsort((m, key))
     want_entries = (((b[order] * M + m[order]).astype(np.int64) << 8) | (f[order] // G)).astype(np.uint32)
     counts = np.bincount(key, minlength=nseg)
-    assert_equal(seg_end, np.cumsum(counts), case[0] + " segment ends")
+    assert_equal(seg_start, np.concatenate([[0], np.cumsum(counts)]), case[0] + " segment starts + total")
     got = plan[ent_w:ent_w + len(want_entries)].view(np.uint32)
     if not canonical:                                                      # any order inside a segment
         seg_of = np.repeat(np.arange(nseg), counts)
