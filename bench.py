@@ -310,6 +310,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
+    # every step pays the whole backward, graph transposition included: the steps reuse one graph, and a plan kept
+    # from step to step (tf_conv3d.SHARE_PLANS, meant for the two convolutions of a level) would be skipped work
+    S.tf_conv3d.SHARE_PLANS = False
     cfg = WORKLOADS[args.workload]
     B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
     M = N

@@ -175,8 +175,11 @@ if __name__ == "__main__":
     ap.add_argument("--N", type=int, default=10000)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--model", default="modelnet", choices=["modelnet", "s3dis"])
+    ap.add_argument("--no-share", action="store_true", help="one graph transposition per convolution gradient (tf_conv3d.SHARE_PLANS off)")
     a = ap.parse_args()
+    S.tf_conv3d.SHARE_PLANS = not a.no_share
     rec = run(a.B, a.N, a.steps, model=a.model)
+    rec["share_plans"] = bool(S.tf_conv3d.SHARE_PLANS)
     print(json.dumps(rec))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "bench_%s.json" % ("encoder" if a.model == "modelnet" else "s3dis")), "w"), indent=1)
+    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "bench_%s%s.json" % ("encoder" if a.model == "modelnet" else "s3dis", "_noshare" if a.no_share else "")), "w"), indent=1)

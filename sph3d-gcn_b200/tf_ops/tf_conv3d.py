@@ -108,16 +108,58 @@ def depthwise_conv3d_grad_planned(input, filter, grad_output, nn_count, plan, nn
     return grad_input, grad_filter
 
 
+# Plan sharing.  The reference's models apply two convolutions per level over one graph (models/SPH3D_*.py call
+# separable_conv3d twice with the same nn_index / nn_count / filt_index), so their two gradients can share one
+# transposed graph.  With SHARE_PLANS on, the plan is built at the first backward pass that needs it and kept as an
+# attribute of the bin_index tensor OBJECT (it lives and dies with the graph; in-place edits of an index tensor change
+# its _version and invalidate it).  bench.py switches this off: its steps reuse one graph, and a plan surviving
+# from step to step would be work skipped inside the timed region.
+SHARE_PLANS = True
+
+
+def _shared_plan(nn_index, nn_count, bin_index, num_bins, npoint):
+    key = (int(num_bins), int(npoint), tuple(nn_index.shape), nn_index.data_ptr(), nn_count.data_ptr(),
+           nn_index._version, nn_count._version, bin_index._version)
+    cache = getattr(bin_index, "_sph3d_plans", None)
+    if cache is not None and key in cache:
+        return cache[key]
+    plan = conv_transpose(nn_index, nn_count, bin_index, num_bins, npoint)
+    try:
+        bin_index._sph3d_plans = {key: plan}          # one plan per graph: a changed key replaces the stale one
+    except Exception:                                    # objects that refuse attributes: no sharing, still correct
+        pass
+    return plan
+
+
+def _use_planned(C, r):
+    """whether a shared plan pays for this layer: always for r = 1 (the one-call form transposes anyway); for r = 2 the
+    transposed form gathers C*r floats per edge and wins only for narrow layers"""
+    return r == 1 or (r == 2 and C * r <= 128)
+
+
 class _DepthwiseConv3d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, filter, nn_index, nn_count, bin_index):
         ctx.save_for_backward(input, filter, nn_index, nn_count, bin_index)
+        ctx.graph = (nn_index, nn_count, bin_index)      # the tensor OBJECTS (a shared plan hangs off bin_index)
         return _forward(input, filter, nn_index, nn_count, bin_index)
 
     @staticmethod
     def backward(ctx, grad_output):
         input, filter, nn_index, nn_count, bin_index = ctx.saved_tensors
-        gi, gf = depthwise_conv3d_grad(input, filter, grad_output.contiguous(), nn_index, nn_count, bin_index)
+        grad_output = grad_output.contiguous()
+        F, C, r = filter.shape
+        if SHARE_PLANS and _use_planned(C, r):
+            g_idx, g_cnt, g_bin = ctx.graph
+            L = _lib.lib()
+            B, N = input.shape[0], input.shape[1]
+            M, K = g_idx.shape[1], g_idx.shape[2]
+            if L.sph3d_depthwise_conv3d_grad_planned_workspace_bytes(B, N, M, F, C, r, K) > 0:
+                plan = _shared_plan(g_idx, g_cnt, g_bin, F, N)
+                if plan is not None:
+                    gi, gf = depthwise_conv3d_grad_planned(input, filter, grad_output, g_cnt, plan, K)
+                    return gi, gf, None, None, None
+        gi, gf = depthwise_conv3d_grad(input, filter, grad_output, nn_index, nn_count, bin_index)
         return gi, gf, None, None, None
 
 

@@ -341,6 +341,39 @@ def test_conv_backward_unequal_clouds_and_garbage_padding(pkg, oracle):
     assert_close(A(gi), ti, 1e-5, "grad_input M != N"); assert_close(A(gf), tf, 1e-5, "grad_filter M != N")
 
 
+def test_plan_sharing_between_the_convolutions_of_a_level(pkg, oracle):
+    """two convolutions over ONE graph (what the models do per level) share one transposed graph, built at the first
+    backward that needs it; an in-place edit of the graph invalidates it"""
+    assert pkg.tf_conv3d.SHARE_PLANS
+    B, N, K, C = 2, 700, 32, 64
+    xyz, q, radius, idx, cnt, dst, filt = _graph(oracle, 76, B, N, K)
+    x, W1, W2 = features(77, B, N, C), features(78, 33, C, 1), features(79, 33, C, 2)
+    g1, g2 = features(80, B, N, C), features(81, B, N, 2 * C)
+    ti1, tf1 = oracle.depthwise_conv3d_grad(x, W1, g1, idx, cnt, filt)
+    ti2, tf2 = oracle.depthwise_conv3d_grad(x, W2, g2, idx, cnt, filt)
+    tidx, tcnt, tfilt = T(idx), T(cnt), T(filt)
+    xt, W1t, W2t = T(x).requires_grad_(True), T(W1).requires_grad_(True), T(W2).requires_grad_(True)
+    o1 = pkg.tf_conv3d.depthwise_conv3d(xt, W1t, tidx, tcnt, tfilt)
+    o2 = pkg.tf_conv3d.depthwise_conv3d(xt, W2t, tidx, tcnt, tfilt)
+    (o1 * T(g1)).sum().backward(retain_graph=True)
+    plans = getattr(tfilt, "_sph3d_plans")
+    assert len(plans) == 1
+    plan_obj = next(iter(plans.values()))
+    gx1 = xt.grad.clone(); xt.grad = None
+    (o2 * T(g2)).sum().backward()
+    assert next(iter(tfilt._sph3d_plans.values())) is plan_obj              # reused, not rebuilt (C*r = 128: planned form)
+    assert_close(A(gx1), ti1, 1e-5, "shared plan: grad_input conv 1"); assert_close(A(W1t.grad), tf1, 1e-5, "grad_filter conv 1")
+    assert_close(A(xt.grad), ti2, 1e-5, "shared plan: grad_input conv 2"); assert_close(A(W2t.grad), tf2, 1e-5, "grad_filter conv 2")
+    # edit the graph in place: the stale plan must not be used
+    cnt2 = cnt.copy(); cnt2[:, ::3] = np.maximum(cnt2[:, ::3] // 2, 1)
+    tcnt.copy_(T(cnt2))
+    ti3, tf3 = oracle.depthwise_conv3d_grad(x, W1, g1, idx, cnt2, filt)
+    xt3 = T(x).requires_grad_(True); W3t = T(W1).requires_grad_(True)
+    (pkg.tf_conv3d.depthwise_conv3d(xt3, W3t, tidx, tcnt, tfilt) * T(g1)).sum().backward()
+    assert next(iter(tfilt._sph3d_plans.values())) is not plan_obj
+    assert_close(A(xt3.grad), ti3, 1e-5, "rebuilt plan: grad_input"); assert_close(A(W3t.grad), tf3, 1e-5, "rebuilt plan: grad_filter")
+
+
 # ------------------------------------------------------------------------------------------ a6 FPS
 FPS_CASES = [("n1024", 3, 1024, 256, "cube"), ("n2048_p2", 2, 2048, 512, "shell"), ("n5000_p5", 2, 5000, 300, "cube"),
              ("n8192_p8", 2, 8192, 2048, "cube"), ("n10000_cs2", 2, 10000, 625, "shell"), ("n20000_cs4", 1, 20000, 200, "cube"),
