@@ -130,6 +130,27 @@ int sph3d_weighted_interpolate_grad(int B, int N, int M, int C, int K, const int
                                     const int* nn_count, const float* grad_output, const float* weight,
                                     float* grad_input, void* stream);
 
+/* ---- a12 (layer tail): bias -> activation -> batch normalisation, utils/sph3gcn_util.py:147-161, :206-220, :257-271
+ * (tf.nn.bias_add, activation_fn = tf.nn.elu, tf.layers.batch_normalization(momentum=0.99) at :328-332).  The reference
+ * runs these as separate TensorFlow graph nodes over the (B*M, C) matmul result; here they are one op whose
+ * intermediate y = act(x + bias) never goes to memory.
+ *   x, out, grad_* : (R, C) row-major, R = B*M.   act: 0 = none, 1 = ELU (alpha 1).
+ *   bias == NULL: no bias.   gamma == NULL: no batch normalisation (beta / moving_* / save_* ignored).
+ *   training != 0: batch statistics (biased variance), moving_* <- moving_* * momentum + batch * (1 - momentum);
+ *   training == 0: the moving statistics normalise.  save_mean / save_invstd (C each) are outputs the gradient needs.
+ * Gradient: grad_bias iff bias, grad_gamma / grad_beta iff gamma; column sums are folded in a fixed order
+ * (bit-reproducible).  workspace: sph3d_bias_act_bn_workspace_bytes(R, C) bytes for either call. */
+size_t sph3d_bias_act_bn_workspace_bytes(int R, int C);
+int sph3d_bias_act_bn(int R, int C, int act, int training, float eps, float momentum,
+                      const float* x, const float* bias, const float* gamma, const float* beta,
+                      float* moving_mean, float* moving_var, float* out, float* save_mean, float* save_invstd,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
+                           const float* x, const float* bias, const float* gamma,
+                           const float* save_mean, const float* save_invstd, const float* grad_out,
+                           float* grad_x, float* grad_bias, float* grad_gamma, float* grad_beta,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ if __package__ in (None, ""):           # flat import from sys.path, the way the
     sys.modules[__name__] = _pkg.utils.sph3gcn_util
 else:
     from ..tf_ops import tf_conv3d, tf_pool3d, tf_unpool3d
+    from . import layer_tail
     from ..tf_ops.tf_nnquery import build_sphere_neighbor, build_cube_neighbor
     from ..tf_ops.tf_sample import farthest_point_sample, inverse_density_sample, random_sample
     from ..tf_ops.tf_buildkernel import spherical_kernel
@@ -217,14 +218,28 @@ else:
 
 
     # ------------------------------------------------------------------ layers
+    # bias -> activation -> BN run as ONE op (csrc/post.cu) whenever the activation is the library's elu or None;
+    # any other callable keeps the node-by-node composition.  FUSED_TAIL = False forces the composition (A/B runs).
+    FUSED_TAIL = True
+
+
     def _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training):
+        fused = FUSED_TAIL and outputs.is_cuda and (activation_fn is None or activation_fn is elu) and \
+            (with_bias or with_bn or activation_fn is not None)
+        biases = _zeros_variable('biases', [num_out_channels], outputs.device) if with_bias else None
+        if fused:
+            act = layer_tail.ACT_ELU if activation_fn is elu else layer_tail.ACT_NONE
+            if with_bn:
+                gamma, beta, moving_mean, moving_var = _bn_variables(num_out_channels, outputs.device, 'bn', reuse)
+                return layer_tail.bias_act_bn(outputs, biases, gamma, beta, moving_mean, moving_var, act=act,
+                                              training=_as_bool(is_training), eps=BN_EPSILON, momentum=BN_MOMENTUM)
+            return layer_tail.bias_act_bn(outputs, biases, act=act)
         if with_bias:
-            biases = _zeros_variable('biases', [num_out_channels], outputs.device)
             outputs = outputs + biases
         if activation_fn is not None:
             outputs = activation_fn(outputs)
         if with_bn:
-            outputs = batch_normalization(outputs, is_training, name='bn', reuse=reuse)
+            outputs = _batch_normalization(outputs, is_training, 'bn', reuse, fused=False)
         return outputs
 
 
@@ -348,19 +363,41 @@ else:
             return outputs
 
 
+    BN_MOMENTUM, BN_EPSILON = 0.99, 1e-3
+
+
+    def _as_bool(is_training):
+        return bool(is_training) if is_training is not None else False
+
+
+    def _bn_variables(C, device, name, reuse):
+        """gamma / beta / moving statistics of one tf.layers.batch_normalization node + its L2 regularizers."""
+        with variable_scope(name, reuse=reuse):
+            gamma = get_variable('gamma', [C], lambda t: t.fill_(1.0), device)
+            beta = get_variable('beta', [C], lambda t: t.zero_(), device)
+            moving_mean = get_variable('moving_mean', [C], lambda t: t.zero_(), device, trainable=False)
+            moving_var = get_variable('moving_variance', [C], lambda t: t.fill_(1.0), device, trainable=False)
+        _STORE.collections["regularization_losses"].append(0.5 * beta.pow(2).sum())
+        _STORE.collections["regularization_losses"].append(0.5 * gamma.pow(2).sum())
+        return gamma, beta, moving_mean, moving_var
+
+
     def batch_normalization(data, is_training, name, reuse=None):
         """tf.layers.batch_normalization(data, momentum=0.99, training=is_training, ...) over the last
         axis, with L2 regularizers (scale 1.0) on beta and gamma (sph3gcn_util.py:328-332)."""
-        momentum, eps = 0.99, 1e-3
+        return _batch_normalization(data, is_training, name, reuse, fused=None)
+
+
+    def _batch_normalization(data, is_training, name, reuse, fused):
+        momentum, eps = BN_MOMENTUM, BN_EPSILON
         C = data.shape[-1]
-        with variable_scope(name, reuse=reuse):
-            gamma = get_variable('gamma', [C], lambda t: t.fill_(1.0), data.device)
-            beta = get_variable('beta', [C], lambda t: t.zero_(), data.device)
-            moving_mean = get_variable('moving_mean', [C], lambda t: t.zero_(), data.device, trainable=False)
-            moving_var = get_variable('moving_variance', [C], lambda t: t.fill_(1.0), data.device, trainable=False)
-        _STORE.collections["regularization_losses"].append(0.5 * beta.pow(2).sum())
-        _STORE.collections["regularization_losses"].append(0.5 * gamma.pow(2).sum())
-        training = bool(is_training) if is_training is not None else False
+        gamma, beta, moving_mean, moving_var = _bn_variables(C, data.device, name, reuse)
+        training = _as_bool(is_training)
+        if fused is None:
+            fused = FUSED_TAIL and data.is_cuda
+        if fused:
+            return layer_tail.bias_act_bn(data, None, gamma, beta, moving_mean, moving_var, act=layer_tail.ACT_NONE,
+                                          training=training, eps=eps, momentum=momentum)
         flat = data.reshape(-1, C)
         if training:
             mean = flat.mean(dim=0)

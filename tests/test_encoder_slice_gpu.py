@@ -1,5 +1,6 @@
-"""Drop-in check at the call sites: the ModelNet encoder of the reference (models/SPH3D_modelnet.py:33-96),
-written against this repository's sph3gcn_util mirror (profiles/bench_encoder.py), runs forward and backward and
+"""Drop-in check at the call sites: the reference's model call graphs (models/SPH3D_modelnet.py, SPH3D_s3dis.py,
+SPH3D_shapenet.py), written against this repository's sph3gcn_util mirror (sph3d-gcn_b200/models, driven by
+profiles/bench_encoder.py), run forward and backward and
 every op inside it agrees with the oracle (odd channel counts 35 / 67 exercise the VEC=1 kernels, the K=N global
 graph the 17-bin kernel)."""
 import os
@@ -43,24 +44,39 @@ def test_separable_conv_odd_channels_matches_oracle(pkg, oracle):
     assert_close(Wd.grad.cpu().numpy(), gf, 2e-5, "grad depthwise_weights through the padded layer")
 
 
-def test_s3dis_encoder_decoder_slice_runs_and_trains(pkg):
-    """segmentation family (models/SPH3D_s3dis.py:35-111): build_graph_deconv, inter-graph ball queries from the fine
-    to the coarse cloud (retries), mean unpooling and skip concats, forward + backward."""
+def test_s3dis_model_slice_runs_and_trains(pkg):
+    """segmentation family (models/SPH3D_s3dis.py:35-133): build_graph_deconv, inter-graph ball queries from the fine
+    to the coarse cloud (retries), mean unpooling and skip concats, inner-point loss, forward + backward."""
     import bench_encoder as be
     B, N = 2, 1024
     rec = be.run(B=B, N=N, steps=1, warmup=1, model="s3dis")
     assert rec["levels"] == [256, 96, 48, 16]
     assert rec["all_grads_finite"] and np.isfinite(rec["loss"])
-    assert rec["feature_dim"] == N * 13                                         # per-point logits
+    assert rec["pred_shape"] == [B, N, 13]                                      # per-point logits
+    assert rec["feature_dim"] == 128 + 128                                      # unpooled deconv4_2 (+) conv1_2 skip
     names = set(pkg.sph3gcn_util.named_variables())
     for want in ("conv4_2/depthwise_weights", "deconv1_1/depthwise_weights", "deconv4_2/weights", "logits/weights"):
         assert want in names, want
     v = pkg.sph3gcn_util.named_variables()
+    assert tuple(v["mlp1/weights"].shape) == (3, 64)                             # normalised xyz only: points[:, :, 6:] is empty
     assert tuple(v["deconv2_1/depthwise_weights"].shape) == (33, 512 + 512, 2)      # unpooled 512 (+) skip 512
     assert all(float(p.grad.abs().sum()) > 0 for n, p in v.items() if n.endswith("depthwise_weights"))
 
 
-def test_modelnet_encoder_slice_runs_and_trains(pkg):
+def test_shapenet_model_slice_runs_and_trains(pkg):
+    """models/SPH3D_shapenet.py:33-123 at K=32 (BASELINE.json configs[2]): raw 6-column input, mlp2 (+) mlp1 before the logits"""
+    import bench_encoder as be
+    B, N = 2, 1024
+    rec = be.run(B=B, N=N, steps=1, warmup=1, model="shapenet")
+    assert rec["levels"] == [512, 384, 192, 64] and rec["K"] == 32
+    assert rec["all_grads_finite"] and np.isfinite(rec["loss"])
+    assert rec["pred_shape"] == [B, N, 50]
+    v = pkg.sph3gcn_util.named_variables()
+    assert tuple(v["mlp1/weights"].shape) == (6, 64) and tuple(v["mlp2/weights"].shape) == (256, 64)
+    assert tuple(v["logits/weights"].shape) == (64 + 64, 50)
+
+
+def test_modelnet_model_slice_runs_and_trains(pkg):
     import bench_encoder as be
     rec = be.run(B=2, N=2048, steps=1, warmup=1)
     assert rec["levels"] == [512, 128]
@@ -68,12 +84,13 @@ def test_modelnet_encoder_slice_runs_and_trains(pkg):
     u = pkg.sph3gcn_util
     names = set(u.named_variables())
     for want in ("mlp1/weights", "conv1_1/depthwise_weights", "conv1_1/weights", "conv2_2/depthwise_weights",
-                 "global_conv/depthwise_weights", "conv1_1/bn/gamma"):
+                 "global_conv/depthwise_weights", "conv1_1/bn/gamma", "fc1/weights", "fc2/bn/beta", "logits/weights"):
         assert want in names, want
     v = u.named_variables()
     assert tuple(v["conv1_1/depthwise_weights"].shape) == (33, 35, 2)         # mlp 32 + raw xyz 3, multiplier 2
     assert tuple(v["conv2_1/depthwise_weights"].shape) == (33, 67, 1)
     assert tuple(v["global_conv/depthwise_weights"].shape) == (17, 128, 2)
     assert all(float(p.grad.abs().sum()) > 0 for n, p in v.items() if n.endswith("depthwise_weights"))
-    # feature vector = 64 + 128 (level maxima) + 512 (global conv)
-    assert rec["feature_dim"] == 64 + 128 + 512
+    # feature vector = 64 + 128 (level maxima) + 512 (global conv); classifier 704 -> 512 -> 256 -> 40
+    assert rec["feature_dim"] == 64 + 128 + 512 and rec["pred_shape"] == [2, 40]
+    assert tuple(v["fc1/weights"].shape) == (704, 512)

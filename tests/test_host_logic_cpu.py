@@ -109,3 +109,33 @@ def test_errors_mirror_the_glue(u, pkg):
         u.pool3d(torch.zeros(1, 2, 3), None, None, 'p', 'median')
     with pytest.raises(ValueError):
         u.unpool3d(torch.zeros(1, 2, 3), None, None, None, 'p', 'cubic')
+
+
+def test_model_helpers_cpu(pkg):
+    """pure-torch pieces of the model call graphs (no custom op involved)"""
+    M = pkg.models
+    torch.manual_seed(1)
+    pts = torch.rand(3, 50, 3) * 4 + 1
+    n = M.SPH3D_modelnet.normalize_xyz(pts)                       # SPH3D_modelnet.py:11-17
+    assert torch.allclose(n.mean(1), torch.zeros(3, 3), atol=1e-6)
+    assert torch.allclose(n.norm(dim=-1).amax(1), torch.ones(3), atol=1e-6)
+    s = M.SPH3D_s3dis.normalize_xyz(pts)                          # SPH3D_s3dis.py:11-19: xy centred on the bbox, z kept
+    assert torch.allclose(s[:, :, 2], pts[:, :, 2])
+    assert torch.allclose(s[:, :, :2].amax(1), -s[:, :, :2].amin(1), atol=1e-6)
+    # S3DIS loss: per cloud mean over inner points, 0 for a cloud without inner points, summed over the batch (:116-130)
+    loss = torch.rand(3, 50)
+    inner = (torch.rand(3, 50) < 0.5).int()
+    inner[1] = 0
+    want = sum(loss[b][inner[b] > 0].mean() for b in (0, 2))
+    assert torch.allclose(M._stages.masked_mean_per_cloud(loss, inner), want, atol=1e-6)
+    pred = torch.randn(3, 50, 13, requires_grad=True)
+    label = torch.randint(0, 13, (3, 50))
+    pkg.sph3gcn_util.reset_variables()
+    got = M.SPH3D_s3dis.get_loss(pred, label, {}, inner)
+    ce = torch.nn.functional.cross_entropy(pred.reshape(-1, 13), label.reshape(-1), reduction='none').reshape(3, 50)
+    assert torch.allclose(got, sum(ce[b][inner[b] > 0].mean() for b in (0, 2)), atol=1e-6)
+    assert pkg.sph3gcn_util.get_collection('losses')[0] is got
+    c = M.configs.s3dis(8192)
+    assert c.num_sample == [2048, 768, 384, 128] and c.binSize == 33
+    assert M.configs.modelnet(10000).num_sample == [2500, 625, 156]
+    assert M.configs.shapenet(2048).num_sample == [1024, 768, 384, 128]
