@@ -55,7 +55,11 @@ def _run_case(pkg, R, C, with_bias, with_bn, act, training, seed, shift=0.0, lea
     assert_close(out.detach().cpu().numpy().reshape(R, C), want.detach().numpy(), 1e-5, "out " + tag)
     assert_close(xd.grad.cpu().numpy(), xr.grad.numpy(), 1e-5, "grad_x " + tag)
     if with_bias:
-        assert_close(bd.grad.cpu().numpy(), br.grad.numpy(), 1e-5, "grad_bias " + tag)
+        # a column sum of grad_x: the tolerance is relative to the size of the summands (under training-mode BN
+        # without activation the exact sum is 0 and only rounding noise is left)
+        summands = float(xr.grad.abs().sum(0).max())
+        err = np.abs(bd.grad.cpu().numpy().astype(np.float64) - br.grad.numpy())
+        assert err.max() <= 1e-5 * summands, "grad_bias %s: max err %.3e (summands %.3e)" % (tag, err.max(), summands)
     if with_bn:
         assert_close(gd.grad.cpu().numpy(), gr.grad.numpy(), 1e-5, "grad_gamma " + tag)
         assert_close(bed.grad.cpu().numpy(), ber.grad.numpy(), 1e-5, "grad_beta " + tag)
