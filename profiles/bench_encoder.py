@@ -36,7 +36,7 @@ def make_config(model, N, K=None):
 DEFAULT_SHAPE = {"modelnet": (32, 10000), "shapenet": (16, 2048), "s3dis": (8, 8192)}
 
 
-def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None):
+def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None, graph=False):
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(seed)
     cfg = make_config(model, N, K)
@@ -69,14 +69,17 @@ def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None):
         loss.backward()
         return pred, end, loss
 
+    run_step = step
+    if graph:                                                 # the whole step as ONE CUDA graph (utils/graph_step.py)
+        run_step = S.utils.graph_step.GraphedStep(step, s3g_util.trainable_variables, warmup=warmup)
     for _ in range(warmup):
-        pred, end, loss = step()
+        pred, end, loss = run_step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
-        pred, end, loss = step()
+        pred, end, loss = run_step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -89,7 +92,7 @@ def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None):
             "ms_per_step": ms, "points_per_s": B * N / (ms * 1e-3), "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
             "pred_shape": list(pred.shape), "feature_dim": int(feat.shape[-1]), "loss": float(loss.detach()), "n_params": len(grads),
             "all_grads_finite": bool(all(gr is not None and torch.isfinite(gr).all() for gr in grads)),
-            "fused_tail": bool(s3g_util.FUSED_TAIL)}
+            "fused_tail": bool(s3g_util.FUSED_TAIL), "cuda_graph": bool(graph)}
 
 
 if __name__ == "__main__":
@@ -101,15 +104,16 @@ if __name__ == "__main__":
     ap.add_argument("--model", default="modelnet", choices=["modelnet", "shapenet", "s3dis"])
     ap.add_argument("--no-share", action="store_true", help="one graph transposition per convolution gradient (tf_conv3d.SHARE_PLANS off)")
     ap.add_argument("--no-fused-tail", action="store_true", help="bias/ELU/BN as separate torch nodes (sph3gcn_util.FUSED_TAIL off)")
+    ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph and time replays")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
     S.tf_conv3d.SHARE_PLANS = not a.no_share
     s3g_util.FUSED_TAIL = not a.no_fused_tail
     B0, N0 = DEFAULT_SHAPE[a.model]
-    rec = run(a.B or B0, a.N or N0, a.steps, model=a.model, K=a.K or None)
+    rec = run(a.B or B0, a.N or N0, a.steps, model=a.model, K=a.K or None, graph=a.graph)
     rec["share_plans"] = bool(S.tf_conv3d.SHARE_PLANS)
     print(json.dumps(rec))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     name = "bench_%s%s%s%s.json" % ("encoder" if a.model == "modelnet" else a.model, "_noshare" if a.no_share else "",
-                                    "_eagertail" if a.no_fused_tail else "", a.tag)
+                                    "_eagertail" if a.no_fused_tail else "", ("_graph" if a.graph else "") + a.tag)
     json.dump(rec, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)

@@ -202,42 +202,47 @@ post_pass_kernel(const PostArgs a)
 
 // Fold the P per-CTA (n, mean, M2) records of every channel (fixed order, fp64), emit mean / invstd and move the
 // moving statistics (tf.layers.batch_normalization: moving = moving*momentum + batch*(1-momentum), biased variance).
-// CTA = 32 channels x 8 slices of the partial list.
-__global__ void __launch_bounds__(256)
+// CTA = 32 channels x 32 slices of the partial list.  Two sweeps over the (L2-resident) records instead of a chain of
+// Chan joins: mean = sum n_p m_p / sum n_p, then M2 = sum [M2_p + n_p (m_p - mean)^2] -- no division inside the loops.
+constexpr int FOLD_SLICES = 32;
+
+__device__ __forceinline__ double fold_slices(double v, double (*sh)[32], int lane, int sl)
+{
+    sh[sl][lane] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int s = 0; s < FOLD_SLICES; s++) t += sh[s][lane];       // same order in every thread of the column
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(32 * FOLD_SLICES)
 post_fold_stats_kernel(int P, int C, float eps, float momentum, const float* __restrict__ part,
                        float* __restrict__ mean, float* __restrict__ invstd,
                        float* __restrict__ moving_mean, float* __restrict__ moving_var)
 {
-    __shared__ double sn[8][32], sm[8][32], sM[8][32];
+    __shared__ double sh[FOLD_SLICES][32];
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
-    double n = 0.0, m = 0.0, M2 = 0.0;
-    if (c < C) {
-        for (int p = sl; p < P; p += 8) {
-            const float* rec = part + (size_t)p * 3 * C + c;
-            const double nb = rec[0];
-            if (nb > 0.0) {
-                const double mb = rec[C], Mb = rec[2 * (size_t)C];
-                const double nn = n + nb, d = mb - m;
-                m += d * (nb / nn);
-                M2 += Mb + d * d * (n * nb / nn);
-                n = nn;
-            }
-        }
+    const int cc = c < C ? c : 0;
+    double n = 0.0, nm = 0.0;
+    for (int p = sl; p < P; p += FOLD_SLICES) {
+        const float* rec = part + (size_t)p * 3 * C + cc;
+        const double nb = rec[0];
+        n += nb;
+        nm += nb * (double)rec[C];
     }
-    sn[sl][lane] = n; sm[sl][lane] = m; sM[sl][lane] = M2;
-    __syncthreads();
+    n = fold_slices(n, sh, lane, sl);
+    nm = fold_slices(nm, sh, lane, sl);
+    const double m = n > 0.0 ? nm / n : 0.0;
+    double M2 = 0.0;
+    for (int p = sl; p < P; p += FOLD_SLICES) {
+        const float* rec = part + (size_t)p * 3 * C + cc;
+        const double d = (double)rec[C] - m;
+        M2 += (double)rec[2 * (size_t)C] + (double)rec[0] * d * d;
+    }
+    M2 = fold_slices(M2, sh, lane, sl);
     if (sl == 0 && c < C) {
-        n = 0.0; m = 0.0; M2 = 0.0;
-        for (int s = 0; s < 8; s++) {
-            const double nb = sn[s][lane];
-            if (nb > 0.0) {
-                const double nn = n + nb, d = sm[s][lane] - m;
-                m += d * (nb / nn);
-                M2 += sM[s][lane] + d * d * (n * nb / nn);
-                n = nn;
-            }
-        }
         const double var = n > 0.0 ? M2 / n : 0.0;
         mean[c] = (float)m;
         invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -259,26 +264,23 @@ __global__ void post_eval_stats_kernel(int C, float eps, const float* __restrict
 }
 
 // out_k[c] = sum_p part[p][k][c], fixed order, fp64 accumulation; NQ in {1, 2}
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FOLD_SLICES)
 post_fold_sums_kernel(int P, int C, int NQ, const float* __restrict__ part, float* __restrict__ out0,
                       float* __restrict__ out1)
 {
-    __shared__ double s0[8][32], s1[8][32];
+    __shared__ double sh[FOLD_SLICES][32];
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
+    const int cc = c < C ? c : 0;
     double a0 = 0.0, a1 = 0.0;
-    if (c < C) {
-        for (int p = sl; p < P; p += 8) {
-            const float* rec = part + (size_t)p * NQ * C + c;
-            a0 += rec[0];
-            if (NQ > 1) a1 += rec[C];
-        }
+    for (int p = sl; p < P; p += FOLD_SLICES) {
+        const float* rec = part + (size_t)p * NQ * C + cc;
+        a0 += rec[0];
+        if (NQ > 1) a1 += rec[C];
     }
-    s0[sl][lane] = a0; s1[sl][lane] = a1;
-    __syncthreads();
+    a0 = fold_slices(a0, sh, lane, sl);
+    if (NQ > 1) a1 = fold_slices(a1, sh, lane, sl);
     if (sl == 0 && c < C) {
-        a0 = 0.0; a1 = 0.0;
-        for (int s = 0; s < 8; s++) { a0 += s0[s][lane]; a1 += s1[s][lane]; }
         if (out0) out0[c] = (float)a0;
         if (NQ > 1 && out1) out1[c] = (float)a1;
     }
@@ -361,7 +363,7 @@ extern "C" int sph3d_bias_act_bn(int R, int C, int act, int training, float eps,
     if (has_bn) {
         if (training) {
             if ((rc = launch_pass<PASS_STATS>(p, act, a, st)) != 0) return rc;
-            post_fold_stats_kernel<<<(C + 31) / 32, 256, 0, st>>>(p.P, C, eps, momentum, a.part, save_mean, save_invstd,
+            post_fold_stats_kernel<<<(C + 31) / 32, 32 * FOLD_SLICES, 0, st>>>(p.P, C, eps, momentum, a.part, save_mean, save_invstd,
                                                                   moving_mean, moving_var);
             SPH3D_CHECK_LAUNCH();
             launches += 2;
@@ -399,7 +401,7 @@ extern "C" int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
     int launches = 0, rc;
     if (has_bn) {
         if ((rc = launch_pass<PASS_BSUMS>(p, act, a, st)) != 0) return rc;
-        post_fold_sums_kernel<<<(C + 31) / 32, 256, 0, st>>>(p.P, C, 2, a.part, grad_beta, grad_gamma);
+        post_fold_sums_kernel<<<(C + 31) / 32, 32 * FOLD_SLICES, 0, st>>>(p.P, C, 2, a.part, grad_beta, grad_gamma);
         SPH3D_CHECK_LAUNCH();
         launches += 2;
     }
@@ -407,7 +409,7 @@ extern "C" int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
     if ((rc = launch_pass<PASS_BAPPLY>(p, act, a, st)) != 0) return rc;
     launches += 1;
     if (bias) {
-        post_fold_sums_kernel<<<(C + 31) / 32, 256, 0, st>>>(p.P, C, 1, a.part, grad_bias, nullptr);
+        post_fold_sums_kernel<<<(C + 31) / 32, 32 * FOLD_SLICES, 0, st>>>(p.P, C, 1, a.part, grad_bias, nullptr);
         SPH3D_CHECK_LAUNCH();
         launches += 1;
     }

@@ -1,0 +1,1 @@
+from . import graph_step   # noqa: F401

@@ -94,3 +94,44 @@ def test_modelnet_model_slice_runs_and_trains(pkg):
     # feature vector = 64 + 128 (level maxima) + 512 (global conv); classifier 704 -> 512 -> 256 -> 40
     assert rec["feature_dim"] == 64 + 128 + 512 and rec["pred_shape"] == [2, 40]
     assert tuple(v["fc1/weights"].shape) == (704, 512)
+
+
+def test_graphed_step_equals_eager_step(pkg):
+    """utils/graph_step.GraphedStep: the whole S3DIS training step (ball queries, FPS on its side stream, bins,
+    convolutions, unpooling, inner-point loss, backward) captured in one CUDA graph; replays on NEW input data must
+    reproduce the eager step (float atomics in the gradients: tolerance)."""
+    from common import assert_close
+    u, M = pkg.sph3gcn_util, pkg.models
+    dev = torch.device("cuda", 0)
+    B, N = 2, 1024
+    cfg = M.configs.s3dis(N)
+    g = torch.Generator().manual_seed(21)
+    pts = torch.rand(B, N, 6, generator=g).to(dev)
+    label = torch.randint(0, 13, (B, N), generator=g).to(dev)
+    inner = (torch.rand(B, N, generator=g) < 0.6).int().to(dev)
+    u.reset_variables()
+
+    def step():
+        u.clear_collections()
+        for p in u.trainable_variables():
+            p.grad = None
+        pred, end = M.SPH3D_s3dis.get_model(pts, True, cfg)
+        loss = M.SPH3D_s3dis.get_loss(pred, label, end, inner)
+        loss.backward()
+        return pred, loss
+
+    gstep = pkg.utils.graph_step.GraphedStep(step, u.trainable_variables, warmup=2)
+    for seed in (22, 23):
+        pts.copy_(torch.rand(B, N, 6, generator=torch.Generator().manual_seed(seed)))
+        pred_g, loss_g = gstep()
+        torch.cuda.synchronize()
+        got = [pred_g.detach().cpu().numpy().copy(), float(loss_g)] + \
+              [p.grad.detach().cpu().numpy().copy() for p in u.trainable_variables()]
+        pred_e, loss_e = step()                                   # eager, same data, same weights
+        want = [pred_e.detach().cpu().numpy(), float(loss_e)] + [p.grad.cpu().numpy() for p in u.trainable_variables()]
+        assert abs(got[1] - want[1]) <= 1e-5 * abs(want[1])
+        assert_close(got[0], want[0], 1e-4, "logits, graph replay vs eager")
+        names = list(u.named_variables())
+        for nme, a, w in zip(names, got[2:], want[2:]):
+            assert_close(a, w, 2e-3, "grad of %s, graph replay vs eager" % nme)
+    assert gstep.replays == 2

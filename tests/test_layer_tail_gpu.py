@@ -113,6 +113,7 @@ def test_layer_library_fused_tail_equals_composition(pkg):
     u = pkg.sph3gcn_util
     torch.manual_seed(11)
     x = torch.randn(4, 900, 48, device="cuda:0")
+    wgt = torch.randn(4, 900, 64, device="cuda:0")
     res = []
     for fused in (True, False):
         u.reset_variables()
@@ -124,7 +125,7 @@ def test_layer_library_fused_tail_equals_composition(pkg):
             with torch.no_grad():
                 u.named_variables()['pw/biases'].add_(0.3)
             y = u.pointwise_conv3d(xg, 64, 'pw', with_bn=True, with_bias=True, is_training=True)
-            (y * torch.linspace(-1, 1, 64, device="cuda:0")).sum().backward()
+            (y * wgt).sum().backward()                  # per-element weights: a per-channel weight has zero gradient through BN
             v = u.named_variables()
             b = u.get_variable_store().buffers
             res.append([y.detach().cpu().numpy(), xg.grad.cpu().numpy()] +
