@@ -15,7 +15,7 @@ def normalize_xyz(points):
     return points / reach
 
 
-def get_model(points, is_training, config=None):
+def _network(points, is_training, config):
     """points (B, N, 3) -> (logits (B, num_cls), end_points)"""
     B, N = points.shape[0], points.shape[1]
     assert N == config.num_input
@@ -46,6 +46,12 @@ def get_model(points, is_training, config=None):
     net = s3g_util.fully_connected(net, config.num_cls, scope='logits', with_bn=False, with_bias=config.with_bias,
                                    activation_fn=None, is_training=is_training)
     return net, end_points
+
+
+def get_model(points, is_training, config=None):
+    # the samplers of build_graph run ahead on a side stream; gather_nd (the only consumer of `indices` here) joins them
+    with s3g_util.async_sampling():
+        return _network(points, is_training, config)
 
 
 def get_loss(pred, label, end_points):

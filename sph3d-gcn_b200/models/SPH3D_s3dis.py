@@ -15,7 +15,7 @@ def normalize_xyz(points):
     return torch.cat((points[:, :, 0:2] - centre[:, :, 0:2], points[:, :, 2:]), dim=2)
 
 
-def get_model(points, is_training, config=None):
+def _network(points, is_training, config):
     """points (B, N, >=3): xyz first; columns 6.. (if any) join the normalised xyz as input features (:36-43)"""
     end_points = {}
     xyz = points[:, :, 0:3].contiguous()
@@ -28,6 +28,12 @@ def get_model(points, is_training, config=None):
     net = s3g_util.pointwise_conv3d(net, config.num_cls, scope='logits', with_bn=False, with_bias=config.with_bias,
                                     activation_fn=None, is_training=is_training)
     return net, end_points
+
+
+def get_model(points, is_training, config=None):
+    # the samplers of build_graph run ahead on a side stream; gather_nd (the only consumer of `indices` here) joins them
+    with s3g_util.async_sampling():
+        return _network(points, is_training, config)
 
 
 def get_loss(pred, label, end_points, inner_label):

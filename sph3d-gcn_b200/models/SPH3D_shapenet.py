@@ -9,7 +9,7 @@ from . import _stages
 from .SPH3D_modelnet import normalize_xyz   # noqa: F401  (same centroid / unit-sphere normalisation, unused when config.normalize is False)
 
 
-def get_model(points, num_cls, is_training, config=None):
+def _network(points, num_cls, is_training, config):
     end_points = {}
     xyz = points[:, :, 0:3].contiguous()
     layer = dict(weight_decay=config.weight_decay, with_bn=config.with_bn, with_bias=config.with_bias,
@@ -22,6 +22,12 @@ def get_model(points, num_cls, is_training, config=None):
     net = s3g_util.pointwise_conv3d(net, num_cls, scope='logits', with_bn=False, with_bias=config.with_bias,
                                     activation_fn=None, is_training=is_training)
     return net, end_points
+
+
+def get_model(points, num_cls, is_training, config=None):
+    # the samplers of build_graph run ahead on a side stream; gather_nd (the only consumer of `indices` here) joins them
+    with s3g_util.async_sampling():
+        return _network(points, num_cls, is_training, config)
 
 
 def get_loss(pred, label, end_points):

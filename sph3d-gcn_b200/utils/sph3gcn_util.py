@@ -9,7 +9,7 @@ include/sph3d_b200.h.  TensorFlow-isms are re-hosted as follows:
       "scope/name"; a variable is created on first use and re-used afterwards (eager execution
       calls the layer function every step, so `reuse` is accepted and ignored);
   tf.add_to_collection('losses', ...)                 -> get_collection('losses') (cleared by the caller
-      once per step with clear_collections());
+      once per step with clear_collections()); the L2 terms of all variables arrive as one fused entry;
   tf.contrib.layers.xavier_initializer()              -> Glorot uniform with TF's fan computation;
   tf.layers.batch_normalization(momentum=0.99)        -> batch norm over the last axis, eps 1e-3,
       biased batch variance, moving statistics updated with 0.99 decay, L2 terms of beta/gamma in
@@ -51,6 +51,7 @@ else:
             self.params = OrderedDict()       # name -> torch.nn.Parameter
             self.buffers = OrderedDict()      # name -> tensor (BN moving statistics)
             self.collections = {"losses": [], "regularization_losses": []}
+            self.pending_l2 = {"losses": [], "regularization_losses": []}   # (variable, scale) L2 terms, see get_collection
             self.scope = []
 
         def full_name(self, name):
@@ -79,12 +80,48 @@ else:
         return OrderedDict(_STORE.params)
 
 
+    class _L2Sum(torch.autograd.Function):
+        """sum_i scale_i * tf.nn.l2_loss(v_i) = sum_i scale_i * |v_i|^2 / 2 over a LIST of variables with multi-tensor
+        kernels: two or three launches per direction instead of four small kernels per variable and direction."""
+        @staticmethod
+        def forward(ctx, scales, *variables):
+            ctx.scales = scales
+            ctx.save_for_backward(*variables)
+            norms = torch.stack(torch._foreach_norm(list(variables), 2))
+            return 0.5 * (norms * norms * _device_constant(scales, norms.device)).sum()
+
+        @staticmethod
+        def backward(ctx, g):
+            grads = torch._foreach_mul(list(ctx.saved_tensors), list(ctx.scales))
+            torch._foreach_mul_(grads, g)
+            return (None,) + tuple(grads)
+
+
+    _CONSTANTS = {}
+
+    def _device_constant(values, device):
+        """small read-only device vector, uploaded once (a per-step H2D copy could not be captured in a CUDA graph)"""
+        key = (tuple(values), device.type, device.index)
+        if key not in _CONSTANTS:
+            _CONSTANTS[key] = torch.tensor(values, dtype=torch.float32, device=device)
+        return _CONSTANTS[key]
+
+
     def get_collection(name):
+        """tf.get_collection.  The per-variable L2 terms (weight decay, BN regularizers) registered since the last
+        clear_collections() are materialised here as ONE fused term: only their sum is ever consumed
+        (tf.add_n(tf.get_collection('losses')) in the reference's train scripts)."""
+        pending = _STORE.pending_l2.get(name)
+        if pending:
+            _STORE.collections[name].append(_L2Sum.apply(tuple(sc for _, sc in pending), *[v for v, _ in pending]))
+            del pending[:]
         return list(_STORE.collections.get(name, []))
 
 
     def clear_collections():
         for v in _STORE.collections.values():
+            del v[:]
+        for v in _STORE.pending_l2.values():
             del v[:]
 
 
@@ -136,7 +173,7 @@ else:
                 torch.nn.init.trunc_normal_(t, mean=0.0, std=stddev, a=-2 * stddev, b=2 * stddev)
         var = get_variable(name, shape, initializer, device)
         if with_decay is not None:
-            _STORE.collections["losses"].append(0.5 * var.pow(2).sum() * with_decay)   # tf.nn.l2_loss * decay
+            _STORE.pending_l2["losses"].append((var, float(with_decay)))               # tf.nn.l2_loss * decay
         return var
 
 
@@ -160,17 +197,70 @@ else:
         return _SIDE_STREAMS[key]
 
 
+    # Deferred sampling.  FPS is `num_sample` sequential rounds on one SM per cloud (1.2 ms for 8192 -> 2048 points), far
+    # longer than the ball query it is enqueued next to, and nothing needs its result before the level's pooling step.
+    # Inside `with async_sampling():` build_graph leaves the sampler (and the construction of `indices`) running on the
+    # side stream and returns at once; the current stream joins when `indices` is first consumed through gather_nd --
+    # the only way the reference's models consume it (tf.gather_nd, models/SPH3D_s3dis.py:68-72) -- or, at the latest,
+    # when the `with` block ends.  Outside the block build_graph joins before it returns (safe for any consumer).
+    _ASYNC_SAMPLING = [False]
+    _PENDING_SAMPLES = []          # (event, indices tensor) not yet joined
+
+
+    @contextlib.contextmanager
+    def async_sampling():
+        old = _ASYNC_SAMPLING[0]
+        _ASYNC_SAMPLING[0] = True
+        try:
+            yield
+        finally:
+            _ASYNC_SAMPLING[0] = old
+            if not old:
+                join_pending_samples()
+
+
+    def join_pending_samples():
+        """make the current stream wait for every sampler still running on the side stream"""
+        while _PENDING_SAMPLES:
+            event, indices = _PENDING_SAMPLES.pop()
+            cur = torch.cuda.current_stream(indices.device)
+            cur.wait_event(event)
+            indices.record_stream(cur)
+
+
+    def _join_sample(indices):
+        event = getattr(indices, "_sph3d_ready", None)
+        if event is not None:
+            cur = torch.cuda.current_stream(indices.device)
+            cur.wait_event(event)
+            indices.record_stream(cur)
+            indices._sph3d_ready = None
+            for i, (ev, _) in enumerate(_PENDING_SAMPLES):
+                if ev is event:
+                    del _PENDING_SAMPLES[i]
+                    break
+
+
+    def _sample_indices(sample_index, batch_size, num_sample):
+        batch_indices = torch.arange(batch_size, device=sample_index.device, dtype=sample_index.dtype)
+        batch_indices = batch_indices.view(-1, 1, 1).expand(-1, int(num_sample), 1)
+        return torch.cat([batch_indices, sample_index.unsqueeze(2)], dim=2)       # (B,S,2) = [batch, point]
+
+
     def build_graph(xyz, radius, nn_uplimit, num_sample, sample_method=None):
         # FPS depends only on xyz and occupies one SM per cloud for `num_sample` sequential rounds, so it is
         # enqueued FIRST on a side stream and overlaps the ball query (which fills the other SMs); the main
-        # stream waits for it before `indices` is built.  Same results, shorter critical path.
+        # stream waits for it before this function returns (or later, see async_sampling).  Same results, shorter
+        # critical path.
         fps_event = None
+        batch_size = xyz.shape[0]
         if num_sample is not None and sample_method == 'FPS' and xyz.is_cuda:
             cur = torch.cuda.current_stream(xyz.device)
             side = _side_stream(xyz.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 sample_index = farthest_point_sample(num_sample, xyz)
+                indices = _sample_indices(sample_index, batch_size, num_sample)
                 fps_event = torch.cuda.Event()
                 fps_event.record(side)
             xyz.record_stream(side)
@@ -178,24 +268,24 @@ else:
         intra_idx, intra_cnt, intra_dst = neighbor_fn(xyz, xyz, radius=radius, nnsample=nn_uplimit)
 
         if num_sample is not None:
+            if fps_event is not None:
+                if _ASYNC_SAMPLING[0]:
+                    indices._sph3d_ready = fps_event
+                    _PENDING_SAMPLES.append((fps_event, indices))
+                else:
+                    cur.wait_event(fps_event)
+                    indices.record_stream(cur)
+                return intra_idx, intra_cnt, intra_dst, indices
             if sample_method == 'random':
                 sample_index = random_sample(num_sample, xyz)
             elif sample_method == 'FPS':
-                if fps_event is not None:
-                    cur.wait_event(fps_event)
-                    sample_index.record_stream(cur)
-                else:
-                    sample_index = farthest_point_sample(num_sample, xyz)
+                sample_index = farthest_point_sample(num_sample, xyz)
             elif sample_method == 'IDS':
                 prob = intra_dst.sum(dim=-1) / intra_cnt.to(torch.float32)
                 sample_index = inverse_density_sample(num_sample, prob)
             else:
                 raise ValueError('Unknown sampling method.')
-
-            batch_size = xyz.shape[0]
-            batch_indices = torch.arange(batch_size, device=xyz.device, dtype=sample_index.dtype)
-            batch_indices = batch_indices.view(-1, 1, 1).expand(-1, int(num_sample), 1)
-            indices = torch.cat([batch_indices, sample_index.unsqueeze(2)], dim=2)   # (B,S,2) = [batch, point]
+            indices = _sample_indices(sample_index, batch_size, num_sample)
         else:
             indices = None
 
@@ -212,6 +302,7 @@ else:
         """tf.gather_nd(params, indices) for the (B,S,2) = [batch, point] indices build_graph returns:
         the row selection the models apply to xyz / intra_idx / intra_cnt / intra_dst
         (models/SPH3D_s3dis.py:68-72)."""
+        _join_sample(indices)
         b = indices[..., 0].long()
         s = indices[..., 1].long()
         return params[b, s].contiguous()
@@ -377,8 +468,7 @@ else:
             beta = get_variable('beta', [C], lambda t: t.zero_(), device)
             moving_mean = get_variable('moving_mean', [C], lambda t: t.zero_(), device, trainable=False)
             moving_var = get_variable('moving_variance', [C], lambda t: t.fill_(1.0), device, trainable=False)
-        _STORE.collections["regularization_losses"].append(0.5 * beta.pow(2).sum())
-        _STORE.collections["regularization_losses"].append(0.5 * gamma.pow(2).sum())
+        _STORE.pending_l2["regularization_losses"] += [(beta, 1.0), (gamma, 1.0)]
         return gamma, beta, moving_mean, moving_var
 
 

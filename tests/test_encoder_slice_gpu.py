@@ -135,3 +135,30 @@ def test_graphed_step_equals_eager_step(pkg):
         for nme, a, w in zip(names, got[2:], want[2:]):
             assert_close(a, w, 2e-3, "grad of %s, graph replay vs eager" % nme)
     assert gstep.replays == 2
+
+
+def test_async_sampling_joins_before_indices_are_read(pkg, oracle):
+    """with async_sampling(): build_graph returns while FPS still runs on the side stream; gather_nd must join it.
+    The gathered rows are checked against the oracle's FPS for a cloud large enough that FPS outlasts the query."""
+    from common import assert_equal, make_cloud
+    u = pkg.sph3gcn_util
+    B, N, S = 4, 8192, 2048
+    xyz_np = make_cloud(171, B, N, "cube")
+    xyz = torch.from_numpy(xyz_np).to("cuda:0")
+    want = oracle.farthest_point_sample(S, xyz_np)                               # (B, S) ids
+    rows = np.take_along_axis(xyz_np, want[:, :, None].astype(np.int64).repeat(3, axis=2), axis=1)
+    for _ in range(3):
+        with u.async_sampling():
+            idx, cnt, dst, indices = u.build_graph(xyz, 0.05, 16, S, sample_method='FPS')
+            assert getattr(indices, "_sph3d_ready", None) is not None            # not joined yet
+            picked = u.gather_nd(xyz, indices)
+            assert indices._sph3d_ready is None
+        assert_equal(picked.cpu().numpy(), rows, "xyz rows selected by async FPS")
+        assert_equal(indices[..., 1].cpu().numpy(), want, "FPS ids")
+    with u.async_sampling():                                                     # never consumed: joined when the block ends
+        _, _, _, indices = u.build_graph(xyz, 0.05, 16, S, sample_method='FPS')
+    assert not u._PENDING_SAMPLES
+    assert_equal(indices[..., 1].cpu().numpy(), want, "FPS ids, joined at block exit")
+    _, _, _, indices = u.build_graph(xyz, 0.05, 16, S, sample_method='FPS')      # outside the block: joined on return
+    assert getattr(indices, "_sph3d_ready", None) is None
+    assert_equal(indices[..., 1].cpu().numpy(), want, "FPS ids, synchronous")

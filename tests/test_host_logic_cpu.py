@@ -139,3 +139,24 @@ def test_model_helpers_cpu(pkg):
     assert c.num_sample == [2048, 768, 384, 128] and c.binSize == 33
     assert M.configs.modelnet(10000).num_sample == [2500, 625, 156]
     assert M.configs.shapenet(2048).num_sample == [1024, 768, 384, 128]
+
+
+def test_l2_terms_are_fused_but_sum_like_the_reference(u):
+    """weight decay: sum_i decay * l2_loss(W_i) (sph3gcn_util.py:79-84); BN regularizers: l2_loss(beta) + l2_loss(gamma)"""
+    torch.manual_seed(2)
+    x = torch.randn(2, 30, 5)
+    y = u.pointwise_conv3d(x, 8, 'a', weight_decay=1e-3, with_bn=True, is_training=True)
+    y = u.pointwise_conv3d(y, 4, 'b', weight_decay=2e-3, with_bn=True, is_training=True)
+    v = u.named_variables()
+    losses, regs = u.get_collection('losses'), u.get_collection('regularization_losses')
+    assert len(losses) == 1 and len(regs) == 1
+    want = 0.5e-3 * v['a/weights'].pow(2).sum() + 1e-3 * v['b/weights'].pow(2).sum()
+    assert torch.allclose(losses[0], want, rtol=1e-6)
+    want_r = sum(0.5 * v[k].pow(2).sum() for k in ('a/bn/gamma', 'a/bn/beta', 'b/bn/gamma', 'b/bn/beta'))
+    assert torch.allclose(regs[0], want_r, rtol=1e-6)
+    (losses[0] * 3.0).backward()
+    assert torch.allclose(v['a/weights'].grad, 3e-3 * v['a/weights'].detach(), rtol=1e-6)
+    assert torch.allclose(v['b/weights'].grad, 6e-3 * v['b/weights'].detach(), rtol=1e-6)
+    assert u.get_collection('losses') == losses              # asking again adds nothing
+    u.clear_collections()
+    assert u.get_collection('losses') == [] and u.get_collection('regularization_losses') == []
