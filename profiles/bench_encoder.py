@@ -36,7 +36,8 @@ def make_config(model, N, K=None):
 DEFAULT_SHAPE = {"modelnet": (32, 10000), "shapenet": (16, 2048), "s3dis": (8, 8192)}
 
 
-def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None, graph=False):
+def make_step(B, N, seed=7, model="modelnet", K=None):
+    """-> (step function, config).  step() = clear collections, forward, the reference's loss, backward."""
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(seed)
     cfg = make_config(model, N, K)
@@ -69,6 +70,11 @@ def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None, graph=False):
         loss.backward()
         return pred, end, loss
 
+    return step, cfg
+
+
+def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None, graph=False):
+    step, cfg = make_step(B, N, seed, model, K)
     run_step = step
     if graph:                                                 # the whole step as ONE CUDA graph (utils/graph_step.py)
         run_step = S.utils.graph_step.GraphedStep(step, s3g_util.trainable_variables, warmup=warmup)

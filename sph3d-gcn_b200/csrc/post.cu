@@ -202,46 +202,52 @@ post_pass_kernel(const PostArgs a)
 
 // Fold the P per-CTA (n, mean, M2) records of every channel (fixed order, fp64), emit mean / invstd and move the
 // moving statistics (tf.layers.batch_normalization: moving = moving*momentum + batch*(1-momentum), biased variance).
-// CTA = 32 channels x 32 slices of the partial list.  Two sweeps over the (L2-resident) records instead of a chain of
-// Chan joins: mean = sum n_p m_p / sum n_p, then M2 = sum [M2_p + n_p (m_p - mean)^2] -- no division inside the loops.
-constexpr int FOLD_SLICES = 32;
+// The records are ~1 MB spread over P rows; a fold is latency-bound, so it wants many loads in flight: a CTA owns only
+// FOLD_CH = 8 channels (one 32-byte sector per record row) and cuts the record list into FOLD_SL = 128 slices.
+// Two sweeps instead of a chain of Chan joins: mean = sum n_p m_p / sum n_p, then M2 = sum [M2_p + n_p (m_p - mean)^2]
+// -- no division inside the loops.
+constexpr int FOLD_CH = 8;
+constexpr int FOLD_SL = 128;
 
-__device__ __forceinline__ double fold_slices(double v, double (*sh)[32], int lane, int sl)
+// sum of v over the FOLD_SL slices of a channel, same value (and same summation order) in every thread of the channel
+__device__ __forceinline__ double fold_slices(double v, double (*sh)[FOLD_CH], int ch, int warp)
 {
-    sh[sl][lane] = v;
+    v += __shfl_xor_sync(FULL_MASK, v, 8);               // a warp holds 4 slices x 8 channels
+    v += __shfl_xor_sync(FULL_MASK, v, 16);
+    if ((threadIdx.x & 31) < FOLD_CH) sh[warp][ch] = v;
     __syncthreads();
     double t = 0.0;
-    for (int s = 0; s < FOLD_SLICES; s++) t += sh[s][lane];       // same order in every thread of the column
+    for (int w = 0; w < FOLD_SL / 4; w++) t += sh[w][ch];
     __syncthreads();
     return t;
 }
 
-__global__ void __launch_bounds__(32 * FOLD_SLICES)
+__global__ void __launch_bounds__(FOLD_CH * FOLD_SL)
 post_fold_stats_kernel(int P, int C, float eps, float momentum, const float* __restrict__ part,
                        float* __restrict__ mean, float* __restrict__ invstd,
                        float* __restrict__ moving_mean, float* __restrict__ moving_var)
 {
-    __shared__ double sh[FOLD_SLICES][32];
-    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
+    __shared__ double sh[FOLD_SL / 4][FOLD_CH];
+    const int ch = threadIdx.x & (FOLD_CH - 1), sl = threadIdx.x / FOLD_CH, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * FOLD_CH + ch;
     const int cc = c < C ? c : 0;
     double n = 0.0, nm = 0.0;
-    for (int p = sl; p < P; p += FOLD_SLICES) {
+    for (int p = sl; p < P; p += FOLD_SL) {
         const float* rec = part + (size_t)p * 3 * C + cc;
         const double nb = rec[0];
         n += nb;
         nm += nb * (double)rec[C];
     }
-    n = fold_slices(n, sh, lane, sl);
-    nm = fold_slices(nm, sh, lane, sl);
+    n = fold_slices(n, sh, ch, warp);
+    nm = fold_slices(nm, sh, ch, warp);
     const double m = n > 0.0 ? nm / n : 0.0;
     double M2 = 0.0;
-    for (int p = sl; p < P; p += FOLD_SLICES) {
+    for (int p = sl; p < P; p += FOLD_SL) {
         const float* rec = part + (size_t)p * 3 * C + cc;
         const double d = (double)rec[C] - m;
         M2 += (double)rec[2 * (size_t)C] + (double)rec[0] * d * d;
     }
-    M2 = fold_slices(M2, sh, lane, sl);
+    M2 = fold_slices(M2, sh, ch, warp);
     if (sl == 0 && c < C) {
         const double var = n > 0.0 ? M2 / n : 0.0;
         mean[c] = (float)m;
@@ -264,22 +270,22 @@ __global__ void post_eval_stats_kernel(int C, float eps, const float* __restrict
 }
 
 // out_k[c] = sum_p part[p][k][c], fixed order, fp64 accumulation; NQ in {1, 2}
-__global__ void __launch_bounds__(32 * FOLD_SLICES)
+__global__ void __launch_bounds__(FOLD_CH * FOLD_SL)
 post_fold_sums_kernel(int P, int C, int NQ, const float* __restrict__ part, float* __restrict__ out0,
                       float* __restrict__ out1)
 {
-    __shared__ double sh[FOLD_SLICES][32];
-    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
+    __shared__ double sh[FOLD_SL / 4][FOLD_CH];
+    const int ch = threadIdx.x & (FOLD_CH - 1), sl = threadIdx.x / FOLD_CH, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * FOLD_CH + ch;
     const int cc = c < C ? c : 0;
     double a0 = 0.0, a1 = 0.0;
-    for (int p = sl; p < P; p += FOLD_SLICES) {
+    for (int p = sl; p < P; p += FOLD_SL) {
         const float* rec = part + (size_t)p * NQ * C + cc;
         a0 += rec[0];
         if (NQ > 1) a1 += rec[C];
     }
-    a0 = fold_slices(a0, sh, lane, sl);
-    if (NQ > 1) a1 = fold_slices(a1, sh, lane, sl);
+    a0 = fold_slices(a0, sh, ch, warp);
+    if (NQ > 1) a1 = fold_slices(a1, sh, ch, warp);
     if (sl == 0 && c < C) {
         if (out0) out0[c] = (float)a0;
         if (NQ > 1 && out1) out1[c] = (float)a1;
@@ -363,7 +369,7 @@ extern "C" int sph3d_bias_act_bn(int R, int C, int act, int training, float eps,
     if (has_bn) {
         if (training) {
             if ((rc = launch_pass<PASS_STATS>(p, act, a, st)) != 0) return rc;
-            post_fold_stats_kernel<<<(C + 31) / 32, 32 * FOLD_SLICES, 0, st>>>(p.P, C, eps, momentum, a.part, save_mean, save_invstd,
+            post_fold_stats_kernel<<<(C + FOLD_CH - 1) / FOLD_CH, FOLD_CH * FOLD_SL, 0, st>>>(p.P, C, eps, momentum, a.part, save_mean, save_invstd,
                                                                   moving_mean, moving_var);
             SPH3D_CHECK_LAUNCH();
             launches += 2;
@@ -401,7 +407,7 @@ extern "C" int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
     int launches = 0, rc;
     if (has_bn) {
         if ((rc = launch_pass<PASS_BSUMS>(p, act, a, st)) != 0) return rc;
-        post_fold_sums_kernel<<<(C + 31) / 32, 32 * FOLD_SLICES, 0, st>>>(p.P, C, 2, a.part, grad_beta, grad_gamma);
+        post_fold_sums_kernel<<<(C + FOLD_CH - 1) / FOLD_CH, FOLD_CH * FOLD_SL, 0, st>>>(p.P, C, 2, a.part, grad_beta, grad_gamma);
         SPH3D_CHECK_LAUNCH();
         launches += 2;
     }
@@ -409,7 +415,7 @@ extern "C" int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
     if ((rc = launch_pass<PASS_BAPPLY>(p, act, a, st)) != 0) return rc;
     launches += 1;
     if (bias) {
-        post_fold_sums_kernel<<<(C + 31) / 32, 32 * FOLD_SLICES, 0, st>>>(p.P, C, 1, a.part, grad_bias, nullptr);
+        post_fold_sums_kernel<<<(C + FOLD_CH - 1) / FOLD_CH, FOLD_CH * FOLD_SL, 0, st>>>(p.P, C, 1, a.part, grad_bias, nullptr);
         SPH3D_CHECK_LAUNCH();
         launches += 1;
     }

@@ -309,6 +309,54 @@ else:
 
 
     # ------------------------------------------------------------------ layers
+    # The pointwise product (tf.matmul over the B*M rows, sph3gcn_util.py:144-146) stays a library GEMM.  Its WEIGHT
+    # gradient x^T g is a (Cin x Cout) result reduced over R = B*M rows: 8-64 output tiles, which cuBLAS runs on as many
+    # SMs without splitting K (measured: 1.35 ms of a 12 ms S3DIS step in `simt_sgemm_64x64_nt` kernels).  Here the rows
+    # are cut into P slabs, one batched GEMM forms the P partial products on all SMs and they are summed in slab order
+    # (deterministic): explicit split-K.
+    SPLIT_K_WEIGHT_GRAD = True
+    _SPLIT_K_MIN_ROWS = 4096
+
+
+    def _weight_grad(x, g):
+        """x (R, Cin), g (R, Cout) -> x^T g (Cin, Cout)"""
+        R, cin = x.shape
+        cout = g.shape[1]
+        if not SPLIT_K_WEIGHT_GRAD or R < _SPLIT_K_MIN_ROWS:
+            return x.t() @ g
+        tiles = ((cin + 63) // 64) * ((cout + 63) // 64)
+        sms = torch.cuda.get_device_properties(x.device).multi_processor_count if x.is_cuda else 148
+        slabs = min(max((2 * sms + tiles - 1) // tiles, 1), R // 512)
+        if slabs <= 1:
+            return x.t() @ g
+        rows = R // slabs
+        main = rows * slabs
+        part = torch.bmm(x[:main].view(slabs, rows, cin).transpose(1, 2), g[:main].view(slabs, rows, cout))
+        out = part.sum(dim=0)
+        if main < R:
+            out = out + x[main:].t() @ g[main:]
+        return out
+
+
+    class _Dense(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            return x @ w
+
+        @staticmethod
+        def backward(ctx, g):
+            x, w = ctx.saved_tensors
+            g = g.contiguous()
+            gx = g @ w.t() if ctx.needs_input_grad[0] else None
+            gw = _weight_grad(x, g) if ctx.needs_input_grad[1] else None
+            return gx, gw
+
+
+    def _dense(x2d, w):
+        return _Dense.apply(x2d.contiguous(), w)
+
+
     # bias -> activation -> BN run as ONE op (csrc/post.cu) whenever the activation is the library's elu or None;
     # any other callable keeps the node-by-node composition.  FUSED_TAIL = False forces the composition (A/B runs).
     FUSED_TAIL = True
@@ -378,7 +426,7 @@ else:
             if pad:
                 kernel = F.pad(kernel, (0, 0, 0, pad * depth_multiplier))
                 num_in_channels += pad * depth_multiplier
-            outputs = torch.matmul(outputs.reshape(-1, num_in_channels), kernel)
+            outputs = _dense(outputs.reshape(-1, num_in_channels), kernel)
             outputs = outputs.reshape(batch_size, -1, num_out_channels)
             return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
 
@@ -401,7 +449,7 @@ else:
             kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
                                                  use_xavier=use_xavier, stddev=stddev,
                                                  with_decay=weight_decay, device=inputs.device)
-            outputs = torch.matmul(inputs.reshape(-1, num_in_channels), kernel)
+            outputs = _dense(inputs.reshape(-1, num_in_channels), kernel)
             outputs = outputs.reshape(batch_size, -1, num_out_channels)
             return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
 
@@ -423,7 +471,7 @@ else:
             kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
                                                  use_xavier=use_xavier, stddev=stddev,
                                                  with_decay=weight_decay, device=inputs.device)
-            outputs = torch.matmul(inputs, kernel)
+            outputs = _dense(inputs, kernel)
             return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
 
 

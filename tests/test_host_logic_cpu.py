@@ -160,3 +160,24 @@ def test_l2_terms_are_fused_but_sum_like_the_reference(u):
     assert u.get_collection('losses') == losses              # asking again adds nothing
     u.clear_collections()
     assert u.get_collection('losses') == [] and u.get_collection('regularization_losses') == []
+
+
+def test_split_k_weight_gradient_matches_plain_product(u):
+    torch.manual_seed(4)
+    for R, cin, cout in ((5000, 70, 24), (4096, 256, 128), (9001, 16, 300), (100, 8, 8)):
+        x, g = torch.randn(R, cin), torch.randn(R, cout)
+        want = (x.double().t() @ g.double())
+        got = u._weight_grad(x, g)
+        assert got.shape == (cin, cout)
+        assert (got.double() - want).abs().max() <= 1e-5 * want.abs().max() + 1e-4
+    # through the layer: same forward value, same gradients as torch.matmul
+    x = torch.randn(3, 2000, 12, requires_grad=True)
+    y = u.pointwise_conv3d(x, 20, 'sk', activation_fn=None)
+    W = u.named_variables()['sk/weights']
+    wgt = torch.randn_like(y)
+    (y * wgt).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    Wr = W.detach().clone().requires_grad_(True)
+    ((xr.reshape(-1, 12) @ Wr).reshape(3, 2000, 20) * wgt).sum().backward()
+    assert torch.allclose(y, (xr.reshape(-1, 12) @ Wr).reshape(3, 2000, 20), atol=1e-6)
+    assert torch.allclose(x.grad, xr.grad, atol=1e-5) and torch.allclose(W.grad, Wr.grad, rtol=1e-4, atol=1e-4)
