@@ -38,7 +38,7 @@ DEFAULT_SHAPE = {"modelnet": (32, 10000), "shapenet": (16, 2048), "s3dis": (8, 8
 
 def make_step(B, N, seed=7, model="modelnet", K=None):
     """-> (step function, config).  step() = clear collections, forward, the reference's loss, backward."""
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     g = torch.Generator().manual_seed(seed)
     cfg = make_config(model, N, K)
     s3g_util.reset_variables()
@@ -73,29 +73,60 @@ def make_step(B, N, seed=7, model="modelnet", K=None):
     return step, cfg
 
 
+def _dist_setup():
+    """torchrun launch (one process per GPU): data-parallel over the batch, SURVEY.md 8(e)"""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world
+
+
 def run(B, N, steps, warmup=2, seed=7, model="modelnet", K=None, graph=False):
-    step, cfg = make_step(B, N, seed, model, K)
+    rank, world = _dist_setup()
+    step, cfg = make_step(B, N, seed + rank, model, K)        # every rank owns B clouds of its own (weak scaling)
     run_step = step
     if graph:                                                 # the whole step as ONE CUDA graph (utils/graph_step.py)
         run_step = S.utils.graph_step.GraphedStep(step, s3g_util.trainable_variables, warmup=warmup)
+    reduced_bytes = 0
+
+    def full_step():
+        """step + (N > 1) the one cross-rank exchange: SUM all-reduce of every weight gradient in one flat bucket"""
+        nonlocal reduced_bytes
+        out = run_step()
+        if world > 1:
+            reduced_bytes = S.utils.dist_util.allreduce_gradients([p.grad for p in s3g_util.trainable_variables()], average=True)
+        return out
+
     for _ in range(warmup):
-        pred, end, loss = run_step()
+        pred, end, loss = full_step()
     torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
-        pred, end, loss = run_step()
+        pred, end, loss = full_step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if world > 1:                                              # max over ranks, on the device clock
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
     grads = [p.grad for p in s3g_util.trainable_variables()]
     what = {"modelnet": "SPH3D_modelnet get_model+get_loss fwd+bwd (configs[1])",
             "shapenet": "SPH3D_shapenet get_model+get_loss fwd+bwd (configs[2])",
             "s3dis": "SPH3D_s3dis get_model+get_loss fwd+bwd (configs[3])"}[model]
     feat = end['global_feat'] if model == "modelnet" else end['feats']
-    return {"workload": what, "B": B, "N": N, "levels": cfg.num_sample, "K": cfg.nn_uplimit[0],
-            "ms_per_step": ms, "points_per_s": B * N / (ms * 1e-3), "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
+    return {"workload": what, "B": B, "N": N, "levels": cfg.num_sample, "K": cfg.nn_uplimit[0], "n_gpus": world,
+            "B_per_gpu": B, "allreduce_bytes_per_step": reduced_bytes,
+            "ms_per_step": ms, "points_per_s": world * B * N / (ms * 1e-3), "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
             "pred_shape": list(pred.shape), "feature_dim": int(feat.shape[-1]), "loss": float(loss.detach()), "n_params": len(grads),
             "all_grads_finite": bool(all(gr is not None and torch.isfinite(gr).all() for gr in grads)),
             "fused_tail": bool(s3g_util.FUSED_TAIL), "cuda_graph": bool(graph)}
@@ -118,8 +149,13 @@ if __name__ == "__main__":
     B0, N0 = DEFAULT_SHAPE[a.model]
     rec = run(a.B or B0, a.N or N0, a.steps, model=a.model, K=a.K or None, graph=a.graph)
     rec["share_plans"] = bool(S.tf_conv3d.SHARE_PLANS)
-    print(json.dumps(rec))
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    name = "bench_%s%s%s%s.json" % ("encoder" if a.model == "modelnet" else a.model, "_noshare" if a.no_share else "",
-                                    "_eagertail" if a.no_fused_tail else "", ("_graph" if a.graph else "") + a.tag)
-    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(rec))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        name = "bench_%s%s%s%s.json" % ("encoder" if a.model == "modelnet" else a.model, "_noshare" if a.no_share else "",
+                                        "_eagertail" if a.no_fused_tail else "", ("_graph" if a.graph else "") +
+                                        ("_dp%d" % rec["n_gpus"] if rec["n_gpus"] > 1 else "") + a.tag)
+        json.dump(rec, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
+    if rec["n_gpus"] > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()

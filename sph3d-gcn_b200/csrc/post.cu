@@ -43,15 +43,27 @@ struct PostArgs {
     float* part;              // [gridDim.y][NQ][C] partials
 };
 
+// ELU as TensorFlow evaluates it (tensorflow/core/kernels/relu_op_functor.h: features < 0 ? exp(features) - 1 : features;
+// gradient (activations + 1) * gradients = exp(features) * gradients): one expf serves value and derivative.  The kernels
+// are instruction-issue bound on this function (ncu: 75 % issue slots busy with expm1f, profiles/r1_layer_tail_ncu.md), so
+// the 10-instruction expf is used rather than the 25-instruction expm1f; |exp(z)-1 - expm1(z)| <= 6e-8.
+template <int ACT> __device__ __forceinline__ void act_eval(float z, float& y, float& der)
+{
+    if constexpr (ACT == POST_ACT_ELU) {
+        const float e = expf(fminf(z, 0.f));
+        const bool pos = z > 0.f;
+        y = pos ? z : e - 1.0f;
+        der = pos ? 1.0f : e;
+    } else {
+        y = z;
+        der = 1.0f;
+    }
+}
 template <int ACT> __device__ __forceinline__ float act_fwd(float z)
 {
-    if constexpr (ACT == POST_ACT_ELU) return z > 0.f ? z : expm1f(z);
-    else return z;
-}
-template <int ACT> __device__ __forceinline__ float act_der(float z)
-{
-    if constexpr (ACT == POST_ACT_ELU) return z > 0.f ? 1.f : expf(z);
-    else return 1.f;
+    float y, d;
+    act_eval<ACT>(z, y, d);
+    return y;
 }
 
 constexpr int POST_WARPS = 8;
@@ -123,7 +135,8 @@ post_pass_kernel(const PostArgs a)
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
                 const float z = xv[u][v] + b[v];
-                const float y = act_fwd<ACT>(z);
+                float y, der;
+                act_eval<ACT>(z, y, der);
                 if (PASS == PASS_STATS) {
                     const float d = y - kshift[v];
                     acc0[v] += d;
@@ -140,7 +153,7 @@ post_pass_kernel(const PostArgs a)
                         const float yh = (y - mu[v]) * is[v];
                         dy = sc[v] * (dy - kb[v] - yh * kg[v]);
                     }
-                    const float dz = dy * act_der<ACT>(z);
+                    const float dz = dy * der;
                     o[v] = dz;
                     acc0[v] += dz;
                 }
