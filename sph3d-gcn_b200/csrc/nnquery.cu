@@ -300,14 +300,19 @@ sphere_query_kernel(int B, int N, int M, int K, float radius0,
         if (mine) myT = range_threshold(r);
     }
     if (!__any_sync(FULL_MASK, mine)) return;                    // the grid kernel owns the whole group
-    float qx[QPW], qy[QPW], qz[QPW], thr[QPW];
+    // negated query coordinates, duplicated into both halves of a register pair: p - q == p + (-q) exactly, and the
+    // distance of TWO database points per lane is then formed with packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2:
+    // the same IEEE operations in the same order as sqdist_ref, half the issue slots -- the scan is issue-bound)
+    float2 nqx[QPW], nqy[QPW], nqz[QPW];
+    float thr[QPW];
     int cnt[QPW];
     bool own[QPW];
 #pragma unroll
     for (int q = 0; q < QPW; q++) {
         int j = min(j0 + q, M - 1);
         const float* qp = query + ((size_t)b * M + j) * 3;
-        qx[q] = __ldg(qp); qy[q] = __ldg(qp + 1); qz[q] = __ldg(qp + 2);
+        const float x = -__ldg(qp), y = -__ldg(qp + 1), z = -__ldg(qp + 2);
+        nqx[q] = make_float2(x, x); nqy[q] = make_float2(y, y); nqz[q] = make_float2(z, z);
         thr[q] = __shfl_sync(FULL_MASK, myT, q);
         own[q] = __shfl_sync(FULL_MASK, mine, q) != 0;
         cnt[q] = own[q] ? 0 : K;                                 // padding / grid-owned queries are "done"
@@ -316,25 +321,36 @@ sphere_query_kernel(int B, int N, int M, int K, float radius0,
     const float* db = database + (size_t)b * N * 3;
     const unsigned lt = (1u << lane) - 1u;
     const float qnan = __int_as_float(0x7fc00000);
-    for (int base = 0; base < N; base += 32) {
-        int k = base + lane;
-        float px = qnan, py = qnan, pz = qnan;
-        if (k < N) { px = __ldg(db + 3 * k); py = __ldg(db + 3 * k + 1); pz = __ldg(db + 3 * k + 2); }
+    for (int base = 0; base < N; base += 64) {                   // lane l: points base+l (.x) and base+32+l (.y)
+        const int k0 = base + lane, k1 = base + 32 + lane;
+        float2 px = make_float2(qnan, qnan), py = px, pz = px;
+        if (k0 < N) { px.x = __ldg(db + 3 * k0); py.x = __ldg(db + 3 * k0 + 1); pz.x = __ldg(db + 3 * k0 + 2); }
+        if (k1 < N) { px.y = __ldg(db + 3 * k1); py.y = __ldg(db + 3 * k1 + 1); pz.y = __ldg(db + 3 * k1 + 2); }
         bool all_done = true;
 #pragma unroll
         for (int q = 0; q < QPW; q++) {
             if (cnt[q] < K) {                                    // warp-uniform
-                float d2 = sqdist_ref(__fsub_rn(px, qx[q]), __fsub_rn(py, qy[q]), __fsub_rn(pz, qz[q]));
-                bool hit = d2 <= thr[q];
-                unsigned m = __ballot_sync(FULL_MASK, hit);
-                if (m) {
-                    int slot = cnt[q] + __popc(m & lt);
-                    if (hit && slot < K) {
-                        size_t o = ((size_t)b * M + (j0 + q)) * K + slot;
-                        nn_index[o] = k;
-                        nn_dist[o] = __fsqrt_rn(__fsqrt_rn(d2));        // Q2: sqrt of the distance
+                const float2 dx = __fadd2_rn(px, nqx[q]), dy = __fadd2_rn(py, nqy[q]), dz = __fadd2_rn(pz, nqz[q]);
+                float2 d2 = __fmul2_rn(dy, dy);                  // Q6: the y product is rounded alone ...
+                d2 = __ffma2_rn(dx, dx, d2);                     // ... the x and z products are fused
+                d2 = __ffma2_rn(dz, dz, d2);
+                const bool hit0 = d2.x <= thr[q], hit1 = d2.y <= thr[q];
+                const unsigned m0 = __ballot_sync(FULL_MASK, hit0), m1 = __ballot_sync(FULL_MASK, hit1);
+                if (m0 | m1) {
+                    const size_t o = ((size_t)b * M + (j0 + q)) * K;
+                    int c = cnt[q];
+                    const int slot0 = c + __popc(m0 & lt);        // ascending index: all of the first half first
+                    if (hit0 && slot0 < K) {
+                        nn_index[o + slot0] = k0;
+                        nn_dist[o + slot0] = __fsqrt_rn(__fsqrt_rn(d2.x));   // Q2: sqrt of the distance
                     }
-                    cnt[q] += __popc(m);
+                    c += __popc(m0);
+                    const int slot1 = c + __popc(m1 & lt);
+                    if (hit1 && slot1 < K) {
+                        nn_index[o + slot1] = k1;
+                        nn_dist[o + slot1] = __fsqrt_rn(__fsqrt_rn(d2.y));
+                    }
+                    cnt[q] = c + __popc(m1);
                 }
                 all_done &= (cnt[q] >= K);
             }
