@@ -1,0 +1,124 @@
+"""Drop-in proof at network scale: the S3DIS and ModelNet call graphs (sph3d-gcn_b200/models) are run twice
+on the same input with the same variables --
+  (a) on this library: sm_100a kernels, fused layer tail, split-K weight gradients, deferred FPS join;
+  (b) with every custom op swapped for the UNMODIFIED reference kernel (oracle/_ref: tf_ops/*/tf_*_gpu.cu compiled as they
+      are, forward and gradient launchers) and the layer tail / matmul as plain torch nodes --
+and logits, loss and every variable's gradient must agree.  Index ops are bit-exact, so both runs build identical graphs;
+what differs is fp32 summation order through ~20 layers (tolerances below are relative to each tensor's scale)."""
+import numpy as np
+import pytest
+import torch
+
+from common import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_ops(ref):
+    """torch.autograd wrappers around the reference launchers (gradients = the reference's own *Grad launchers)"""
+
+    class Conv(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, filter, nn_index, nn_count, bin_index):
+            ctx.save_for_backward(input, filter, nn_index, nn_count, bin_index)
+            return ref.depthwise_conv3d(input.contiguous(), filter.contiguous(), nn_index, nn_count, bin_index)
+
+        @staticmethod
+        def backward(ctx, g):
+            input, filter, nn_index, nn_count, bin_index = ctx.saved_tensors
+            gi, gf = ref.depthwise_conv3d_grad(input.contiguous(), filter.contiguous(), g.contiguous(), nn_index, nn_count, bin_index)
+            return gi, gf, None, None, None
+
+    class MaxPool(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, nn_index, nn_count):
+            out, max_index = ref.max_pool3d(input.contiguous(), nn_index, nn_count)
+            ctx.save_for_backward(input, max_index)
+            ctx.mark_non_differentiable(max_index)
+            return out, max_index
+
+        @staticmethod
+        def backward(ctx, g, _):
+            input, max_index = ctx.saved_tensors
+            return ref.max_pool3d_grad(input.contiguous(), g.contiguous(), max_index), None, None
+
+    class MeanUnpool(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, nn_index, nn_count):
+            ctx.save_for_backward(input, nn_index, nn_count)
+            return ref.mean_interpolate(input.contiguous(), nn_index, nn_count)
+
+        @staticmethod
+        def backward(ctx, g):
+            input, nn_index, nn_count = ctx.saved_tensors
+            return ref.mean_interpolate_grad(input.contiguous(), g.contiguous(), nn_index, nn_count), None, None
+
+    return Conv, MaxPool, MeanUnpool
+
+
+def _run(pkg, model, pts, label, inner, cfg):
+    u, M = pkg.sph3gcn_util, pkg.models
+    u.clear_collections()
+    for p in u.trainable_variables():
+        p.grad = None
+    if model == "s3dis":
+        pred, end = M.SPH3D_s3dis.get_model(pts, True, cfg)
+        loss = M.SPH3D_s3dis.get_loss(pred, label, end, inner)
+    else:
+        pred, end = M.SPH3D_modelnet.get_model(pts, False, cfg)          # inference mode: no dropout, moving statistics
+        loss = M.SPH3D_modelnet.get_loss(pred, label, end)
+    loss = loss + sum(u.get_collection('losses')[1:])                    # + the fused weight-decay term, if any
+    loss.backward()
+    torch.cuda.synchronize()
+    names = list(u.named_variables())
+    grads = [None if p.grad is None else p.grad.detach().cpu().numpy().copy() for p in u.trainable_variables()]
+    return pred.detach().cpu().numpy().copy(), float(loss.detach()), names, grads
+
+
+@pytest.mark.parametrize("model", ["s3dis", "modelnet"])
+def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, monkeypatch, model):
+    if ref is None:
+        pytest.skip("oracle/_ref/libsph3d_ref.so not built")
+    u, M = pkg.sph3gcn_util, pkg.models
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(77)
+    if model == "s3dis":
+        B, N = 2, 1024
+        cfg = M.configs.s3dis(N)
+        pts = torch.rand(B, N, 6, generator=g).to(dev)
+        label = torch.randint(0, 13, (B, N), generator=g).to(dev)
+        inner = (torch.rand(B, N, generator=g) < 0.6).int().to(dev)
+    else:
+        B, N = 2, 2048
+        cfg = M.configs.modelnet(N)
+        pts = torch.rand(B, N, 3, generator=g).to(dev)
+        label = torch.randint(0, 40, (B,), generator=g).to(dev)
+        inner = None
+    u.reset_variables()
+    _run(pkg, model, pts, label, inner, cfg)                             # creates the variables
+    if model == "modelnet":                                              # give the moving statistics non-trivial values
+        for k, t in u.get_variable_store().buffers.items():
+            t.copy_(torch.rand(t.shape, generator=g).to(dev) * 0.5 + (0.75 if k.endswith("variance") else -0.25))
+    pred_a, loss_a, names, grads_a = _run(pkg, model, pts, label, inner, cfg)
+
+    Conv, MaxPool, MeanUnpool = _reference_ops(ref)
+    monkeypatch.setattr(u, "neighbor_fn", ref.build_sphere_neighbor)
+    monkeypatch.setattr(u, "spherical_kernel", ref.spherical_kernel)
+    monkeypatch.setattr(u, "farthest_point_sample", ref.farthest_point_sample)
+    monkeypatch.setattr(u.tf_conv3d, "depthwise_conv3d", lambda i, f, a, b, c: Conv.apply(i, f, a, b, c))
+    monkeypatch.setattr(u.tf_pool3d, "max_pool3d", lambda i, a, b: MaxPool.apply(i, a, b))
+    monkeypatch.setattr(u.tf_unpool3d, "mean_interpolate", lambda i, a, b: MeanUnpool.apply(i, a, b))
+    monkeypatch.setattr(u, "FUSED_TAIL", False)
+    monkeypatch.setattr(u, "SPLIT_K_WEIGHT_GRAD", False)
+    pred_b, loss_b, _, grads_b = _run(pkg, model, pts, label, inner, cfg)
+
+    assert_close(pred_a, pred_b, 1e-3, "%s logits: this library vs reference kernels" % model)
+    assert abs(loss_a - loss_b) <= 1e-4 * abs(loss_b)
+    checked = 0
+    for name, a, b in zip(names, grads_a, grads_b):
+        assert (a is None) == (b is None), name
+        if a is None:
+            continue
+        assert_close(a, b, 2e-2, "%s grad of %s: this library vs reference kernels" % (model, name))
+        checked += 1
+    assert checked >= (60 if model == "s3dis" else 30)
