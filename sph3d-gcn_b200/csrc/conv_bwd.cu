@@ -245,7 +245,7 @@ conv_bwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict
 // plan: vec in {4,2,1}, SLOTS in {9,17}, G in {1,2,4,8} with G*SLOTS >= F and SLOTS*vec*r <= 72 registers
 static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
 {
-    ConvPlan p{0, 0, 0, 0, 0, 0};
+    ConvPlan p{};
     *G_out = 0;
     if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 136) return p;
     int vec = pick_vec_full_warp(C), slots = 0, G = 0;
@@ -280,11 +280,13 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     p.threads = tune_int("SPH3D_BWD_THREADS", max_threads);
     if (p.threads > max_threads || p.threads % (32 * G)) p.threads = max_threads;
     const long long rows = (long long)B * M;
-    const int rpc = rows_per_chunk();
-    const long long nchunks = (rows + rpc - 1) / rpc;
     long long want = sm_count();
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;
     if (want < 1) want = 1;
+    // a warp group walks its rows one after the other: small problems get chunks of >= 2 rows per group so that all SMs work
+    const int rpc = pick_rows_per_chunk(rows, want, 2 * (p.threads / (32 * G)));
+    p.rpc = rpc;
+    const long long nchunks = (rows + rpc - 1) / rpc;
     p.grid_x = (int)(nchunks < want ? nchunks : want);
     while (p.threads > 32 * G && p.threads > 64 &&
            (long long)p.grid_x * p.chunks * (p.threads / (32 * G)) > rows && p.grid_x * p.chunks < sm_count())
@@ -360,7 +362,7 @@ extern "C" int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, in
     if (!workspace || workspace_bytes < P * nW * sizeof(float)) return (int)cudaErrorInvalidValue;
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * M);
-    const unsigned rpc = (unsigned)rows_per_chunk();
+    const unsigned rpc = (unsigned)p.rpc;
     float* part = (float*)workspace;
 #define LAUNCH_BWD(V, RR, SL)                                                                        \
     do {                                                                                             \

@@ -142,6 +142,7 @@ struct ConvPlan {
     int slots;        // backward: filter bins owned per warp
     size_t smem;      // dynamic shared memory bytes
     int cta_reduce;   // backward: groups of a CTA are summed in shared memory before the partial is written
+    int rpc;          // rows per contiguous chunk handed to a CTA
 };
 
 static inline int pick_vec(int C) { return (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1); }
@@ -177,6 +178,23 @@ static inline int tune_int(const char* name, int dflt)
     return x > 0 ? x : dflt;
 }
 static inline int rows_per_chunk() { return tune_int("SPH3D_ROWS_PER_CHUNK", 128); }
+
+// Chunk size for a problem of `rows` rows when `want` CTAs (per channel chunk) would fill the machine.  Large problems
+// keep the default (contiguous rows share neighbours, so long chunks keep the gathers in L1).  Small ones -- the deep
+// levels of the segmentation networks: 1 000-6 000 rows, up to 8 channel chunks -- would leave most SMs idle with
+// 128-row chunks (a 1024-row level is 8 chunks) while each warp walks its rows one after the other; there the chunk
+// shrinks until every SM has one, down to `min_rows` (one row per warp or per warp group).
+static inline int pick_rows_per_chunk(long long rows, long long want, int min_rows)
+{
+    int rpc = rows_per_chunk();
+    if (getenv("SPH3D_ROWS_PER_CHUNK")) return rpc;                  // sweeps pin it
+    const long long nchunks = (rows + rpc - 1) / rpc;
+    if (nchunks >= want) return rpc;
+    long long per = (rows + want - 1) / want;                        // rows per CTA if every SM gets one chunk
+    per = (per + min_rows - 1) / min_rows * min_rows;
+    if (per < min_rows) per = min_rows;
+    return (int)(per < rpc ? per : rpc);
+}
 
 // conv_bwd.cu: out[t] = sum_p part[p][t], fixed order (bit-reproducible)
 int launch_reduce_partials(int P, size_t n, const float* part, float* out, cudaStream_t st);

@@ -162,7 +162,7 @@ conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict
 
 static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
 {
-    ConvPlan p{0, 0, 0, 0, 0, 0};
+    ConvPlan p{};
     if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 128) return p;
     int vec = pick_vec_full_warp(C);
     {   // sweep knob: force a strip width (must divide C)
@@ -177,11 +177,12 @@ static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
     p.vec = vec; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
     const long long rows = (long long)B * M;
-    const int rpc = rows_per_chunk();
-    const long long nchunks = (rows + rpc - 1) / rpc;
     long long want = sm_count();                                   // one persistent 32-warp CTA per SM ...
     if (p.chunks > 1) want = (want + p.chunks - 1) / p.chunks;      // ... shared by the channel chunks
     if (want < 1) want = 1;
+    const int rpc = pick_rows_per_chunk(rows, want, 32);           // small problems: shorter chunks, more CTAs
+    p.rpc = rpc;
+    const long long nchunks = (rows + rpc - 1) / rpc;
     p.grid_x = (int)(nchunks < want ? nchunks : want);
     // small problems: fewer warps per CTA so that more SMs get work
     p.threads = tune_int("SPH3D_FWD_THREADS", 1024);
@@ -216,7 +217,7 @@ extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, 
     }
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * M);
-    const unsigned rpc = (unsigned)rows_per_chunk();
+    const unsigned rpc = (unsigned)p.rpc;
     cudaError_t e = cudaSuccess;
 #define LAUNCH_FWD(V, RR)                                                                           \
     do {                                                                                             \

@@ -115,10 +115,15 @@ def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, m
     assert_close(pred_a, pred_b, 1e-3, "%s logits: this library vs reference kernels" % model)
     assert abs(loss_a - loss_b) <= 1e-4 * abs(loss_b)
     checked = 0
+    # gradients that are ~1e-11 next to others of ~1e-1 (BN parameters in front of a max-pool that lets almost nothing
+    # through) are rounding noise in BOTH runs: the absolute floor is 1e-6 of the largest gradient entry of the network
+    floor = 1e-6 * max(float(np.abs(b).max()) for b in grads_b if b is not None)
     for name, a, b in zip(names, grads_a, grads_b):
         assert (a is None) == (b is None), name
         if a is None:
             continue
-        assert_close(a, b, 2e-2, "%s grad of %s: this library vs reference kernels" % (model, name))
+        err = np.abs(a.astype(np.float64) - b)
+        tol = 2e-2 * float(np.abs(b).max()) + floor
+        assert err.max() <= tol, "%s grad of %s: max err %.3e > %.3e (scale %.3e)" % (model, name, err.max(), tol, np.abs(b).max())
         checked += 1
     assert checked >= (60 if model == "s3dis" else 30)
