@@ -30,7 +30,8 @@ extern "C" {
 #define SPH3D_B200_ABI_VERSION 2
 int sph3d_abi_version(void);
 
-/* Number of KERNELS (memsets excluded) the most recent entry-point call enqueued (bench.py gpu_launches). */
+/* Number of KERNELS (memsets excluded) the calling thread's most recent entry-point call enqueued (bench.py
+ * gpu_launches).  The counter is thread-local: every entry point is reentrant. */
 int sph3d_last_launch_count(void);
 
 /* ---- a1: buildSphereNeighborLauncher, tf_nnquery_gpu.cu:115-121 (kernel :15-65) --------------

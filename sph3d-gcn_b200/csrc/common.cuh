@@ -25,7 +25,7 @@ __host__ inline int sm_count()
 }
 
 // counts kernels enqueued by the most recent C-ABI call (bench.py's gpu_launches evidence)
-extern int g_last_launch_count;
+extern thread_local int g_last_launch_count;   // per host thread: the entry points stay reentrant
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -25,7 +25,7 @@
 
 namespace sph3d {
 
-int g_last_launch_count = 0;
+thread_local int g_last_launch_count = 0;
 
 template <int VEC, int R>
 __global__ void __launch_bounds__(1024, 1)
