@@ -152,6 +152,18 @@ int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
                            float* grad_x, float* grad_bias, float* grad_gamma, float* grad_beta,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a12 (pointwise product): tf.matmul over the B*M rows, utils/sph3gcn_util.py:144-146, :203-205, :254-256 --------
+ * fp32 in, fp32 out, fp32 accuracy, on tcgen05 tensor cores: each operand tile is split on chip into three BF16 terms and
+ * all nine cross products are accumulated in TMEM (csrc/dense_gemm.cuh).  D[l] (M x N, row-major, packed over l < L) =
+ *   op 0:  A[l] (M x K row-major) * B[l] (K x N row-major)                       y  = x * w
+ *   op 1:  A[l] (M x K row-major) * B[l]^T with B[l] (N x K row-major)           gx = g * w^T
+ *   op 2:  A[l]^T with A[l] (K x M row-major) * B[l] (K x N row-major)           gw = x^T * g, L = row slabs (split-K)
+ * M, N, K multiples of 4 and 16-byte aligned pointers (TMA), else cudaErrorInvalidValue (1): the caller keeps such shapes
+ * on its library GEMM.  Returns cudaErrorNotSupported (801) when the library was built without the CUTLASS header tree. */
+size_t sph3d_dense_gemm_workspace_bytes(int op, int M, int N, int K, int L);
+int sph3d_dense_gemm(int op, int M, int N, int K, int L, const float* A, const float* B, float* D,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ SIGNATURES = {
     "sph3d_bias_act_bn_workspace_bytes": (c_size_t, [c_int] * 2),
     "sph3d_bias_act_bn": (c_int, [c_int] * 4 + [c_float] * 2 + [_P] * 10 + [c_size_t, _P]),
     "sph3d_bias_act_bn_grad": (c_int, [c_int] * 4 + [_P] * 11 + [c_size_t, _P]),
+    "sph3d_dense_gemm_workspace_bytes": (c_size_t, [c_int] * 5),
+    "sph3d_dense_gemm": (c_int, [c_int] * 5 + [_P] * 4 + [c_size_t, _P]),
 }
 
 

@@ -14,10 +14,43 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsph3d_b200.so")
-SOURCES = ["nnquery.cu", "buildkernel.cu", "conv_fwd.cu", "conv_bwd.cu", "conv_bwd_t.cu", "pool3d.cu", "sample.cu", "post.cu"]
-HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
+SOURCES = ["nnquery.cu", "buildkernel.cu", "conv_fwd.cu", "conv_bwd.cu", "conv_bwd_t.cu", "pool3d.cu", "sample.cu", "post.cu",
+           "dense_nn.cu", "dense_nt.cu", "dense_tn.cu", "dense_abi.cu"]
+HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", "dense_gemm.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
+
+
+def cutlass_root():
+    """CuTe/CUTLASS header tree vendored in the image (no /opt/cutlass): the dense_*.cu translation units instantiate
+    its sm_100 tcgen05 collectives.  Returns the directory that holds include/ and tools/util/include, or None."""
+    import importlib.util
+    cands = []
+    env = os.environ.get("SPH3D_CUTLASS_ROOT")
+    if env:
+        cands.append(env)
+    for pkg, rel in (("flashinfer", os.path.join("data", "cutlass")), ("tilelang", os.path.join("3rdparty", "cutlass"))):
+        try:
+            spec = importlib.util.find_spec(pkg)
+        except Exception:
+            spec = None
+        if spec and spec.submodule_search_locations:
+            cands.append(os.path.join(list(spec.submodule_search_locations)[0], rel))
+    for c in cands:
+        if os.path.exists(os.path.join(c, "include", "cutlass", "gemm", "collective", "builders", "sm100_9xBF16_umma_builder.inl")) \
+                and os.path.exists(os.path.join(c, "tools", "util", "include", "cutlass", "util", "packed_stride.hpp")):
+            return c
+    return None
+
+
+def _extra_flags(source):
+    if not source.startswith("dense_"):
+        return []
+    root = cutlass_root()
+    if root is None:                                   # entry points still exist and return cudaErrorNotSupported
+        return ["-DSPH3D_NO_CUTLASS"]
+    return ["-I", os.path.join(root, "include"), "-I", os.path.join(root, "tools", "util", "include"),
+            "--expt-relaxed-constexpr", "-w"]
 
 
 def _nvcc():
@@ -47,7 +80,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, s)]
+        cmd = [_nvcc()] + NVCC_FLAGS + _extra_flags(s) + ["-c", "-o", obj, os.path.join(CSRC, s)]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -316,6 +316,32 @@ else:
     # (deterministic): explicit split-K.
     SPLIT_K_WEIGHT_GRAD = True
     _SPLIT_K_MIN_ROWS = 4096
+    # The three products of a layer (y = x w, gx = g w^T, gw = x^T g) run on the tcgen05 tensor cores at fp32 accuracy
+    # (csrc/dense_gemm.cuh: operands split on chip into three BF16 terms, nine cross products accumulated in TMEM) when the
+    # shape allows TMA (channel counts multiples of 4) and the problem is large enough to fill the machine; anything else --
+    # the 3-channel input layer, the 13/40/50-class logits, CPU tensors -- stays on the library GEMM.
+    TENSOR_CORE_DENSE = True
+    _TC_MIN_ROWS = 2048
+
+
+    def _tc_gemm(op, a, b, M, N, K, L=1):
+        """D[l] = A[l] B[l] in the layouts of include/sph3d_b200.h (sph3d_dense_gemm); None when the shape is not covered"""
+        from .. import _lib
+        if not (TENSOR_CORE_DENSE and a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32):
+            return None
+        if M % 4 or N % 4 or K % 4 or (a.data_ptr() | b.data_ptr()) % 16:
+            return None
+        lib = _lib.lib()
+        out = torch.empty((L, M, N) if L > 1 else (M, N), dtype=torch.float32, device=a.device)
+        ws_bytes = lib.sph3d_dense_gemm_workspace_bytes(op, M, N, K, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
+        with torch.cuda.device(a.device):
+            rc = lib.sph3d_dense_gemm(op, M, N, K, L, _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                                      _lib.stream_ptr())
+        if rc in (1, 801):                                 # shape not implementable / built without the tensor-core path
+            return None
+        _lib.check(rc, "dense_gemm")
+        return out
 
 
     def _weight_grad(x, g):
@@ -324,14 +350,17 @@ else:
         cout = g.shape[1]
         if not SPLIT_K_WEIGHT_GRAD or R < _SPLIT_K_MIN_ROWS:
             return x.t() @ g
-        tiles = ((cin + 63) // 64) * ((cout + 63) // 64)
+        tiles = ((cin + 127) // 128) * ((cout + 127) // 128) if TENSOR_CORE_DENSE and x.is_cuda else \
+            ((cin + 63) // 64) * ((cout + 63) // 64)
         sms = torch.cuda.get_device_properties(x.device).multi_processor_count if x.is_cuda else 148
         slabs = min(max((2 * sms + tiles - 1) // tiles, 1), R // 512)
         if slabs <= 1:
             return x.t() @ g
-        rows = R // slabs
+        rows = (R // slabs) // 4 * 4                       # slab length a multiple of 4 rows (TMA strides)
         main = rows * slabs
-        part = torch.bmm(x[:main].view(slabs, rows, cin).transpose(1, 2), g[:main].view(slabs, rows, cout))
+        part = _tc_gemm(2, x, g, cin, cout, rows, slabs) if rows >= 4 else None
+        if part is None:
+            part = torch.bmm(x[:main].view(slabs, rows, cin).transpose(1, 2), g[:main].view(slabs, rows, cout))
         out = part.sum(dim=0)
         if main < R:
             out = out + x[main:].t() @ g[main:]
@@ -342,19 +371,27 @@ else:
         @staticmethod
         def forward(ctx, x, w):
             ctx.save_for_backward(x, w)
-            return x @ w
+            R, K = x.shape
+            y = _tc_gemm(0, x, w, R, w.shape[1], K) if R >= _TC_MIN_ROWS else None
+            return y if y is not None else x @ w
 
         @staticmethod
         def backward(ctx, g):
             x, w = ctx.saved_tensors
             g = g.contiguous()
-            gx = g @ w.t() if ctx.needs_input_grad[0] else None
-            gw = _weight_grad(x, g) if ctx.needs_input_grad[1] else None
+            gx = gw = None
+            if ctx.needs_input_grad[0]:
+                R, N = g.shape
+                gx = _tc_gemm(1, g, w, R, w.shape[0], N) if R >= _TC_MIN_ROWS else None
+                if gx is None:
+                    gx = g @ w.t()
+            if ctx.needs_input_grad[1]:
+                gw = _weight_grad(x, g)
             return gx, gw
 
 
     def _dense(x2d, w):
-        return _Dense.apply(x2d.contiguous(), w)
+        return _Dense.apply(x2d.contiguous(), w.contiguous())
 
 
     # bias -> activation -> BN run as ONE op (csrc/post.cu) whenever the activation is the library's elu or None;

@@ -1,0 +1,74 @@
+"""Pointwise product on the tcgen05 tensor cores at fp32 accuracy (csrc/dense_gemm.cuh, C ABI sph3d_dense_gemm) against a
+float64 product.  Tolerance: 1e-5 of the result's scale (north_star), i.e. what the fp32 SIMT GEMM of the reference's
+tf.matmul delivers; a single-pass TF32 or BF16 product would miss it by two orders of magnitude."""
+import numpy as np
+import pytest
+import torch
+
+from common import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops(pkg):
+    return pkg.sph3gcn_util
+
+
+@pytest.mark.parametrize("R,K,N", [(4096, 128, 128), (65536, 256, 128), (3072, 2048, 256), (20000, 72, 64), (2052, 36, 512)])
+def test_forward_and_input_gradient_products(pkg, R, K, N):
+    u = _ops(pkg)
+    g = torch.Generator().manual_seed(R + K + N)
+    x = (torch.randn(R, K, generator=g) * 2 + 0.5).cuda()
+    w = (torch.randn(K, N, generator=g) * 0.3).cuda()
+    go = torch.randn(R, N, generator=g).cuda()
+    y = u._tc_gemm(0, x, w, R, N, K)
+    assert y is not None, "tensor-core path refused an aligned shape"
+    assert_close(y.cpu().numpy(), (x.double() @ w.double()).cpu().numpy(), 1e-5, "y = x w (%d,%d,%d)" % (R, K, N))
+    gx = u._tc_gemm(1, go, w, R, K, N)
+    assert gx is not None
+    assert_close(gx.cpu().numpy(), (go.double() @ w.double().t()).cpu().numpy(), 1e-5, "gx = g w^T (%d,%d,%d)" % (R, K, N))
+
+
+@pytest.mark.parametrize("R,K,N", [(65536, 256, 128), (6144, 512, 256), (50001, 72, 64)])
+def test_weight_gradient_split_k(pkg, R, K, N):
+    u = _ops(pkg)
+    g = torch.Generator().manual_seed(R)
+    x = (torch.randn(R, K, generator=g) + 0.25).cuda()
+    go = torch.randn(R, N, generator=g).cuda()
+    gw = u._weight_grad(x, go)
+    assert_close(gw.cpu().numpy(), (x.double().t() @ go.double()).cpu().numpy(), 1e-5, "gw = x^T g (%d,%d,%d)" % (R, K, N))
+    again = u._weight_grad(x, go)
+    assert torch.equal(gw, again)                                   # slabs summed in a fixed order
+
+
+def test_unaligned_shapes_fall_back_to_the_library_gemm(pkg):
+    u = _ops(pkg)
+    x = torch.randn(4096, 3, device="cuda")
+    w = torch.randn(3, 32, device="cuda")
+    assert u._tc_gemm(0, x, w, 4096, 32, 3) is None                  # K = 3: no TMA
+    assert u._tc_gemm(0, torch.randn(4096, 64, device="cuda"), torch.randn(64, 13, device="cuda"), 4096, 13, 64) is None
+    y = u._dense(x, w)
+    assert_close(y.cpu().numpy(), (x.double() @ w.double()).cpu().numpy(), 1e-5, "fallback product")
+
+
+def test_layer_with_and_without_tensor_cores(pkg):
+    """pointwise_conv3d end to end: same outputs and gradients with TENSOR_CORE_DENSE on and off"""
+    u = _ops(pkg)
+    torch.manual_seed(5)
+    x = torch.randn(8, 2048, 64, device="cuda")
+    wgt = torch.randn(8, 2048, 128, device="cuda")
+    res = []
+    for on in (True, False):
+        u.reset_variables()
+        u.TENSOR_CORE_DENSE = on
+        try:
+            torch.manual_seed(6)
+            xg = x.clone().requires_grad_(True)
+            y = u.pointwise_conv3d(xg, 128, 'tc', with_bn=True, is_training=True)
+            (y * wgt).sum().backward()
+            v = u.named_variables()
+            res.append([y.detach().cpu().numpy(), xg.grad.cpu().numpy(), v['tc/weights'].grad.cpu().numpy()])
+        finally:
+            u.TENSOR_CORE_DENSE = True
+    for i, (a, b) in enumerate(zip(*res)):
+        assert_close(a, b, 2e-5, "tensor cores on vs off, item %d" % i)

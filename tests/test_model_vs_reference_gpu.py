@@ -1,6 +1,6 @@
 """Drop-in proof at network scale: the S3DIS and ModelNet call graphs (sph3d-gcn_b200/models) are run twice
 on the same input with the same variables --
-  (a) on this library: sm_100a kernels, fused layer tail, split-K weight gradients, deferred FPS join;
+  (a) on this library: sm_100a kernels, fused layer tail, tcgen05 pointwise products, split-K weight gradients, deferred FPS join;
   (b) with every custom op swapped for the UNMODIFIED reference kernel (oracle/_ref: tf_ops/*/tf_*_gpu.cu compiled as they
       are, forward and gradient launchers) and the layer tail / matmul as plain torch nodes --
 and logits, loss and every variable's gradient must agree.  Index ops are bit-exact, so both runs build identical graphs;
@@ -110,6 +110,7 @@ def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, m
     monkeypatch.setattr(u.tf_unpool3d, "mean_interpolate", lambda i, a, b: MeanUnpool.apply(i, a, b))
     monkeypatch.setattr(u, "FUSED_TAIL", False)
     monkeypatch.setattr(u, "SPLIT_K_WEIGHT_GRAD", False)
+    monkeypatch.setattr(u, "TENSOR_CORE_DENSE", False)
     pred_b, loss_b, _, grads_b = _run(pkg, model, pts, label, inner, cfg)
 
     assert_close(pred_a, pred_b, 1e-3, "%s logits: this library vs reference kernels" % model)
