@@ -10,6 +10,10 @@
 // collective `MainloopSm100TmaUmmaWarpSpecializedFastF32` from the header tree vendored in this image
 // (flashinfer/data/cutlass/include, CUTLASS 4.5), instantiated per operand layout in dense_*.cu.
 //
+// SCHEDULE: KernelTmaWarpSpecialized1SmFastFP32Sm100 keeps the BF16 terms of a K-major A operand in TENSOR MEMORY (the
+// transform warps write them with tcgen05.st; only B's terms go back to shared memory), ...SmemSm100 keeps both in
+// shared memory (required for an M-major A, i.e. the weight gradient).
+//
 // Each instantiation lives at namespace scope (nvcc's host pass cannot size CollectiveEpilogue::SharedStorage from inside
 // a class template) and in its own translation unit (two minutes of template expansion each, compiled in parallel).
 #pragma once
@@ -26,7 +30,7 @@
 #include "cutlass/util/packed_stride.hpp"
 
 // D[l] (M x N, row-major) = A[l] (M x K, LAYOUT_A) * B[l] (K x N, LAYOUT_B), l < L, packed batch strides
-#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B)                                                                     \
+#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B, SCHEDULE)                                                           \
 namespace NS {                                                                                                              \
     using namespace cute;                                                                                                   \
     using LayoutC = cutlass::layout::RowMajor;                                                                              \
@@ -40,7 +44,7 @@ namespace NS {                                                                  
         cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, float, LAYOUT_A, 4, float, LAYOUT_B, 4, float,                \
         MmaTileShape, ClusterShape,                                                                                         \
         cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>, \
-        cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32SmemSm100>::CollectiveOp;                                         \
+        cutlass::gemm::SCHEDULE>::CollectiveOp;                                                                            \
     using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>; \
     using DeviceGemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;                                             \
     using StrideA = typename GemmKernel::StrideA;                                                                           \
@@ -77,7 +81,7 @@ namespace NS {                                                                  
 }
 #else
 // built without the CUTLASS header tree: the entry points exist and report "not supported"
-#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B)                                                                     \
+#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B, SCHEDULE)                                                           \
 namespace NS {                                                                                                              \
     size_t workspace(int, int, int, int) { return 0; }                                                                      \
     int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t) { return (int)cudaErrorNotSupported; } \

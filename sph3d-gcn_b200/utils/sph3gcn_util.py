@@ -331,6 +331,13 @@ else:
             return None
         if M % 4 or N % 4 or K % 4 or (a.data_ptr() | b.data_ptr()) % 16:
             return None
+        if op != 2:
+            # 128 x 128 output tiles, one CTA each: measured (profiles/r1_dense.json) to beat the fp32 SIMT GEMM by
+            # 1.25-1.55x when at least ~64 tiles exist and they are more than half full; a 64-wide output (half-empty
+            # tiles) or a short-and-deep product (3072 x 256 over K = 2048: 48 tiles) is left to the library
+            tiles = ((M + 127) // 128) * ((N + 127) // 128)
+            if tiles < 64 or M * N < 0.55 * tiles * 16384:
+                return None
         lib = _lib.lib()
         out = torch.empty((L, M, N) if L > 1 else (M, N), dtype=torch.float32, device=a.device)
         ws_bytes = lib.sph3d_dense_gemm_workspace_bytes(op, M, N, K, L)
