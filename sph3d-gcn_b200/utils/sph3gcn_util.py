@@ -321,7 +321,6 @@ else:
     # shape allows TMA (channel counts multiples of 4) and the problem is large enough to fill the machine; anything else --
     # the 3-channel input layer, the 13/40/50-class logits, CPU tensors -- stays on the library GEMM.
     TENSOR_CORE_DENSE = True
-    _TC_MIN_ROWS = 2048
 
 
     def _tc_gemm(op, a, b, M, N, K, L=1):
@@ -331,13 +330,6 @@ else:
             return None
         if M % 4 or N % 4 or K % 4 or (a.data_ptr() | b.data_ptr()) % 16:
             return None
-        if op != 2:
-            # 128 x 128 output tiles, one CTA each: measured (profiles/r1_dense.json) to beat the fp32 SIMT GEMM by
-            # 1.25-1.55x when at least ~64 tiles exist and they are more than half full; a 64-wide output (half-empty
-            # tiles) or a short-and-deep product (3072 x 256 over K = 2048: 48 tiles) is left to the library
-            tiles = ((M + 127) // 128) * ((N + 127) // 128)
-            if tiles < 64 or M * N < 0.55 * tiles * 16384:
-                return None
         lib = _lib.lib()
         out = torch.empty((L, M, N) if L > 1 else (M, N), dtype=torch.float32, device=a.device)
         ws_bytes = lib.sph3d_dense_gemm_workspace_bytes(op, M, N, K, L)
@@ -349,6 +341,14 @@ else:
             return None
         _lib.check(rc, "dense_gemm")
         return out
+
+
+    def _tc_pays(M, N):
+        """128 x 128 output tiles, one CTA each: measured (profiles/r1_dense.json) to beat the fp32 SIMT GEMM by 1.25-1.55x
+        when at least ~64 tiles exist and they are more than half full; a 64-wide output (half-empty tiles) or a short and
+        deep product (3072 x 256 over K = 2048: 48 tiles) is left to the library."""
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        return tiles >= 64 and M * N >= 0.55 * tiles * 16384
 
 
     def _weight_grad(x, g):
@@ -365,7 +365,7 @@ else:
             return x.t() @ g
         rows = (R // slabs) // 4 * 4                       # slab length a multiple of 4 rows (TMA strides)
         main = rows * slabs
-        part = _tc_gemm(2, x, g, cin, cout, rows, slabs) if rows >= 4 else None
+        part = _tc_gemm(2, x, g, cin, cout, rows, slabs) if rows >= 4 and cin * cout >= 0.55 * tiles * 16384 else None
         if part is None:
             part = torch.bmm(x[:main].view(slabs, rows, cin).transpose(1, 2), g[:main].view(slabs, rows, cout))
         out = part.sum(dim=0)
@@ -379,7 +379,7 @@ else:
         def forward(ctx, x, w):
             ctx.save_for_backward(x, w)
             R, K = x.shape
-            y = _tc_gemm(0, x, w, R, w.shape[1], K) if R >= _TC_MIN_ROWS else None
+            y = _tc_gemm(0, x, w, R, w.shape[1], K) if _tc_pays(R, w.shape[1]) else None
             return y if y is not None else x @ w
 
         @staticmethod
@@ -389,7 +389,7 @@ else:
             gx = gw = None
             if ctx.needs_input_grad[0]:
                 R, N = g.shape
-                gx = _tc_gemm(1, g, w, R, w.shape[0], N) if R >= _TC_MIN_ROWS else None
+                gx = _tc_gemm(1, g, w, R, w.shape[0], N) if _tc_pays(R, w.shape[0]) else None
                 if gx is None:
                     gx = g @ w.t()
             if ctx.needs_input_grad[1]:
