@@ -158,6 +158,7 @@ int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
  *   op 0:  A[l] (M x K row-major) * B[l] (K x N row-major)                       y  = x * w
  *   op 1:  A[l] (M x K row-major) * B[l]^T with B[l] (N x K row-major)           gx = g * w^T
  *   op 2:  A[l]^T with A[l] (K x M row-major) * B[l] (K x N row-major)           gw = x^T * g, L = row slabs (split-K)
+ *   op 3 / 4: ops 0 / 1 with cta_group::2 (a CTA pair per 256 x 128 tile)
  * M, N, K multiples of 4 and 16-byte aligned pointers (TMA), else cudaErrorInvalidValue (1): the caller keeps such shapes
  * on its library GEMM.  Returns cudaErrorNotSupported (801) when the library was built without the CUTLASS header tree. */
 size_t sph3d_dense_gemm_workspace_bytes(int op, int M, int N, int K, int L);

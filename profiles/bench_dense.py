@@ -35,6 +35,7 @@ def timeit(fn, iters=20, warm=3):
 
 
 def main():
+    u.DENSE_CTA_PAIR = "--pair" in sys.argv          # y / gx on cta_group::2 kernels
     torch.manual_seed(0)
     tot = {"tc": 0.0, "lib": 0.0}
     for R, K, N, where in SHAPES:

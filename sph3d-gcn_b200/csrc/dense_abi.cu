@@ -10,6 +10,8 @@ extern "C" size_t sph3d_dense_gemm_workspace_bytes(int op, int M, int N, int K, 
     case 0: return sph3d_dense_nn::workspace(M, N, K, L);
     case 1: return sph3d_dense_nt::workspace(M, N, K, L);
     case 2: return sph3d_dense_tn::workspace(M, N, K, L);
+    case 3: return sph3d_dense_nn2::workspace(M, N, K, L);
+    case 4: return sph3d_dense_nt2::workspace(M, N, K, L);
     default: return 0;
     }
 }
@@ -27,6 +29,8 @@ extern "C" int sph3d_dense_gemm(int op, int M, int N, int K, int L, const float*
     case 0: rc = sph3d_dense_nn::run(M, N, K, L, A, B, D, workspace, workspace_bytes, st); break;
     case 1: rc = sph3d_dense_nt::run(M, N, K, L, A, B, D, workspace, workspace_bytes, st); break;
     case 2: rc = sph3d_dense_tn::run(M, N, K, L, A, B, D, workspace, workspace_bytes, st); break;
+    case 3: rc = sph3d_dense_nn2::run(M, N, K, L, A, B, D, workspace, workspace_bytes, st); break;
+    case 4: rc = sph3d_dense_nt2::run(M, N, K, L, A, B, D, workspace, workspace_bytes, st); break;
     default: return (int)cudaErrorInvalidValue;
     }
     if (rc == 0) sph3d::g_last_launch_count = 1;

@@ -14,6 +14,10 @@
 // transform warps write them with tcgen05.st; only B's terms go back to shared memory), ...SmemSm100 keeps both in
 // shared memory (required for an M-major A, i.e. the weight gradient).
 //
+// TILE_M / CLUSTER_M / EPILOGUE: _128 / _1 / TmaWarpSpecialized1Sm = one CTA per 128 x 128 tile; _256 / _2 /
+// TmaWarpSpecialized2Sm with a ...2Sm... schedule = cta_group::2, a CTA pair shares one 256 x 128 tile (each CTA loads half
+// of B; the pair's MMA reads both halves).
+//
 // Each instantiation lives at namespace scope (nvcc's host pass cannot size CollectiveEpilogue::SharedStorage from inside
 // a class template) and in its own translation unit (two minutes of template expansion each, compiled in parallel).
 #pragma once
@@ -30,16 +34,16 @@
 #include "cutlass/util/packed_stride.hpp"
 
 // D[l] (M x N, row-major) = A[l] (M x K, LAYOUT_A) * B[l] (K x N, LAYOUT_B), l < L, packed batch strides
-#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B, SCHEDULE)                                                           \
+#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B, SCHEDULE, TILE_M, CLUSTER_M, EPILOGUE)                              \
 namespace NS {                                                                                                              \
     using namespace cute;                                                                                                   \
     using LayoutC = cutlass::layout::RowMajor;                                                                              \
-    using MmaTileShape = Shape<_128, _128, _16>;                                                                            \
-    using ClusterShape = Shape<_1, _1, _1>;                                                                                 \
+    using MmaTileShape = Shape<TILE_M, _128, _16>;                                                                          \
+    using ClusterShape = Shape<CLUSTER_M, _1, _1>;                                                                              \
     using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<                                   \
         cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,                                   \
         cutlass::epilogue::collective::EpilogueTileAuto, float, float, float, LayoutC, 4, float, LayoutC, 4,                \
-        cutlass::epilogue::TmaWarpSpecialized1Sm>::CollectiveOp;                                                            \
+        cutlass::epilogue::EPILOGUE>::CollectiveOp;                                                                        \
     using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<                                       \
         cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, float, LAYOUT_A, 4, float, LAYOUT_B, 4, float,                \
         MmaTileShape, ClusterShape,                                                                                         \
@@ -81,7 +85,7 @@ namespace NS {                                                                  
 }
 #else
 // built without the CUTLASS header tree: the entry points exist and report "not supported"
-#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B, SCHEDULE)                                                           \
+#define SPH3D_DEFINE_FP32_GEMM(NS, LAYOUT_A, LAYOUT_B, SCHEDULE, TILE_M, CLUSTER_M, EPILOGUE)                              \
 namespace NS {                                                                                                              \
     size_t workspace(int, int, int, int) { return 0; }                                                                      \
     int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t) { return (int)cudaErrorNotSupported; } \
@@ -91,3 +95,5 @@ namespace NS {                                                                  
 namespace sph3d_dense_nn { size_t workspace(int, int, int, int); int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t); }
 namespace sph3d_dense_nt { size_t workspace(int, int, int, int); int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t); }
 namespace sph3d_dense_tn { size_t workspace(int, int, int, int); int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t); }
+namespace sph3d_dense_nn2 { size_t workspace(int, int, int, int); int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t); }
+namespace sph3d_dense_nt2 { size_t workspace(int, int, int, int); int run(int, int, int, int, const float*, const float*, float*, void*, size_t, cudaStream_t); }

@@ -321,6 +321,7 @@ else:
     # shape allows TMA (channel counts multiples of 4) and the problem is large enough to fill the machine; anything else --
     # the 3-channel input layer, the 13/40/50-class logits, CPU tensors -- stays on the library GEMM.
     TENSOR_CORE_DENSE = True
+    DENSE_CTA_PAIR = False         # y / gx with cta_group::2 (a CTA pair per 256 x 128 tile): ops 3 / 4 of sph3d_dense_gemm
 
 
     def _tc_gemm(op, a, b, M, N, K, L=1):
@@ -331,6 +332,8 @@ else:
         if M % 4 or N % 4 or K % 4 or (a.data_ptr() | b.data_ptr()) % 16:
             return None
         lib = _lib.lib()
+        if DENSE_CTA_PAIR and op in (0, 1):
+            op += 3
         out = torch.empty((L, M, N) if L > 1 else (M, N), dtype=torch.float32, device=a.device)
         ws_bytes = lib.sph3d_dense_gemm_workspace_bytes(op, M, N, K, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
