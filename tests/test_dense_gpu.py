@@ -14,9 +14,12 @@ def _ops(pkg):
     return pkg.sph3gcn_util
 
 
+@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("R,K,N", [(4096, 128, 128), (65536, 256, 128), (3072, 2048, 256), (20000, 72, 64), (2052, 36, 512)])
-def test_forward_and_input_gradient_products(pkg, R, K, N):
+def test_forward_and_input_gradient_products(pkg, monkeypatch, R, K, N, pair):
+    """pair = cta_group::2 kernels (a CTA pair per 256 x 128 tile, ops 3 / 4), else one CTA per 128 x 128 tile (ops 0 / 1)"""
     u = _ops(pkg)
+    monkeypatch.setattr(u, "DENSE_CTA_PAIR", pair)
     g = torch.Generator().manual_seed(R + K + N)
     x = (torch.randn(R, K, generator=g) * 2 + 0.5).cuda()
     w = (torch.randn(K, N, generator=g) * 0.3).cuda()
