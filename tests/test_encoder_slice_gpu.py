@@ -132,10 +132,13 @@ def test_graphed_step_equals_eager_step(pkg):
         assert abs(got[1] - want[1]) <= 1e-5 * abs(want[1])
         assert_close(got[0], want[0], 1e-4, "logits, graph replay vs eager")
         names = list(u.named_variables())
+        floor = 1e-6 * max(float(np.abs(w).max()) for w in want[2:])
         for nme, a, w in zip(names, got[2:], want[2:]):
             # two runs of the same fp32 network: float-atomic summation order differs, and column sums that cancel
             # (BN beta / gamma gradients of ~1e-7) amplify that noise -- a consistency bound, not a parity bound
-            assert_close(a, w, 2e-2, "grad of %s, graph replay vs eager" % nme)
+            err = np.abs(a.astype(np.float64) - w)
+            tol = 2e-2 * float(np.abs(w).max()) + floor
+            assert err.max() <= tol, "grad of %s, graph replay vs eager: max err %.3e > %.3e" % (nme, err.max(), tol)
     assert gstep.replays == 2
 
 
