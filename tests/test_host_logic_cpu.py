@@ -181,3 +181,15 @@ def test_split_k_weight_gradient_matches_plain_product(u):
     ((xr.reshape(-1, 12) @ Wr).reshape(3, 2000, 20) * wgt).sum().backward()
     assert torch.allclose(y, (xr.reshape(-1, 12) @ Wr).reshape(3, 2000, 20), atol=1e-6)
     assert torch.allclose(x.grad, xr.grad, atol=1e-5) and torch.allclose(W.grad, Wr.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_tensor_core_gate_and_cpu_behaviour(u):
+    """shape gate of the tcgen05 pointwise product (profiles/r1_dense.json) and: no tensor-core path for CPU tensors"""
+    assert u._tc_pays(65536, 128) and u._tc_pays(16384, 256) and u._tc_pays(6144, 256) and u._tc_pays(320000, 72)
+    assert not u._tc_pays(320000, 64)          # half-empty 128-wide tiles
+    assert not u._tc_pays(3072, 256)           # 48 tiles
+    assert not u._tc_pays(1024, 512)
+    x, w = torch.randn(4096, 128), torch.randn(128, 128)
+    assert u._tc_gemm(0, x, w, 4096, 128, 128) is None
+    y = u._dense(x, w)
+    assert torch.allclose(y, x @ w)
