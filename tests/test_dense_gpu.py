@@ -75,3 +75,20 @@ def test_layer_with_and_without_tensor_cores(pkg):
             u.TENSOR_CORE_DENSE = True
     for i, (a, b) in enumerate(zip(*res)):
         assert_close(a, b, 2e-5, "tensor cores on vs off, item %d" % i)
+
+
+def test_layer_products_against_numpy_oracle(pkg):
+    """_Dense (forward + both gradients through autograd) against oracle/oracle_layers.py"""
+    import oracle_layers as OL
+    u = _ops(pkg)
+    rng = np.random.default_rng(8)
+    R, K, N = 16384, 256, 128
+    x, w, go = (rng.standard_normal(s).astype(np.float32) for s in ((R, K), (K, N), (R, N)))
+    xd = torch.from_numpy(x).cuda().requires_grad_(True)
+    wd = torch.from_numpy(w).cuda().requires_grad_(True)
+    y = u._dense(xd, wd)
+    y.backward(torch.from_numpy(go).cuda())
+    gx, gw = OL.dense_grad(x, w, go)
+    assert_close(y.detach().cpu().numpy(), OL.dense(x, w), 1e-5, "y")
+    assert_close(xd.grad.cpu().numpy(), gx, 1e-5, "grad_x")
+    assert_close(wd.grad.cpu().numpy(), gw, 1e-5, "grad_w")

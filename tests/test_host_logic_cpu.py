@@ -193,3 +193,37 @@ def test_tensor_core_gate_and_cpu_behaviour(u):
     assert u._tc_gemm(0, x, w, 4096, 128, 128) is None
     y = u._dense(x, w)
     assert torch.allclose(y, x @ w)
+
+
+def test_layer_oracle_closed_forms_match_autograd():
+    """oracle/oracle_layers.py (numpy float64, gradients written out) against torch autograd of the same composition"""
+    import oracle_layers as OL
+    rng = np.random.default_rng(3)
+    R, C = 257, 12
+    x, go = rng.standard_normal((R, C)) * 1.5, rng.standard_normal((R, C))
+    bias, gamma, beta = rng.standard_normal(C) * 0.3, rng.random(C) + 0.5, rng.standard_normal(C)
+    mm, mv = rng.standard_normal(C) * 0.1, rng.random(C) + 0.5
+    for act in (True, False):
+        for training in (True, False):
+            out, nmm, nmv, cache = OL.bias_act_bn(x, bias, gamma, beta, mm, mv, act=act, training=training)
+            gx, gb, gg, gbe = OL.bias_act_bn_grad(cache, go, act=act, training=training)
+            t = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)
+            xt, bt, gt, bet = t(x), t(bias), t(gamma), t(beta)
+            z = xt + bt
+            y = torch.nn.functional.elu(z) if act else z
+            mean, var = (y.mean(0), y.var(0, unbiased=False)) if training else (torch.tensor(mm), torch.tensor(mv))
+            o = (y - mean) / torch.sqrt(var + 1e-3) * gt + bet
+            o.backward(torch.tensor(go))
+            assert np.allclose(out, o.detach().numpy(), atol=1e-12)
+            for a, b in ((gx, xt.grad), (gb, bt.grad), (gg, gt.grad), (gbe, bet.grad)):
+                assert np.allclose(a, b.numpy(), atol=1e-10)
+            if training:
+                assert np.allclose(nmm, mm * 0.99 + y.detach().numpy().mean(0) * 0.01)
+                assert np.allclose(nmv, mv * 0.99 + y.detach().numpy().var(0) * 0.01)
+    out, _, _, cache = OL.bias_act_bn(x, None, None, None, act=True)            # no bias, no BN: plain ELU
+    assert np.allclose(out, np.where(x > 0, x, np.exp(x) - 1))
+    gx, gb, gg, gbe = OL.bias_act_bn_grad(cache, go, act=True, with_bias=False)
+    assert gb is None and gg is None and np.allclose(gx, go * np.where(x > 0, 1.0, np.exp(x)))
+    w = rng.standard_normal((C, 5))
+    gxd, gwd = OL.dense_grad(x, w, rng.standard_normal((R, 5)))
+    assert gxd.shape == (R, C) and gwd.shape == (C, 5)

@@ -146,3 +146,32 @@ def test_layer_tail_rejects_cpu_and_bad_shapes(pkg):
         lt.bias_act_bn(x, torch.zeros(7, device="cuda:0"))
     with pytest.raises(ValueError):
         lt.bias_act_bn(x, None, torch.ones(8, device="cuda:0"))          # gamma without beta / moving statistics
+
+
+@pytest.mark.parametrize("act,training", [(True, True), (True, False), (False, True)])
+def test_layer_tail_against_numpy_oracle(pkg, act, training):
+    """sph3d_bias_act_bn[_grad] against oracle/oracle_layers.py (float64 numpy, gradients in closed form)"""
+    import oracle_layers as OL
+    lt = pkg.utils.layer_tail
+    rng = np.random.default_rng(41)
+    R, C = 5000, 128
+    x = (rng.standard_normal((R, C)) * 1.3).astype(np.float32)
+    go = rng.standard_normal((R, C)).astype(np.float32)
+    bias = (rng.standard_normal(C) * 0.4).astype(np.float32)
+    gamma, beta = (rng.random(C) + 0.5).astype(np.float32), rng.standard_normal(C).astype(np.float32)
+    mm, mv = (rng.standard_normal(C) * 0.1).astype(np.float32), (rng.random(C) + 0.5).astype(np.float32)
+    want, nmm, nmv, cache = OL.bias_act_bn(x, bias, gamma, beta, mm, mv, act=act, training=training)
+    gx, gb, gg, gbe = OL.bias_act_bn_grad(cache, go, act=act, training=training)
+    d = lambda a, rg=False: torch.from_numpy(a.copy()).to("cuda:0").requires_grad_(rg)
+    xd, bd, gd, bed, mmd, mvd = d(x, True), d(bias, True), d(gamma, True), d(beta, True), d(mm), d(mv)
+    out = lt.bias_act_bn(xd, bd, gd, bed, mmd, mvd, act=lt.ACT_ELU if act else lt.ACT_NONE, training=training)
+    out.backward(d(go))
+    tag = " act=%d train=%d" % (act, training)
+    assert_close(out.detach().cpu().numpy(), want, 1e-5, "out" + tag)
+    assert_close(xd.grad.cpu().numpy(), gx, 1e-5, "grad_x" + tag)
+    assert_close(gd.grad.cpu().numpy(), gg, 1e-5, "grad_gamma" + tag)
+    assert_close(bed.grad.cpu().numpy(), gbe, 1e-5, "grad_beta" + tag)
+    summands = float(np.abs(gx).sum(0).max())
+    assert np.abs(bd.grad.cpu().numpy() - gb).max() <= 1e-5 * summands
+    assert_close(mmd.cpu().numpy(), nmm, 1e-5, "moving_mean" + tag)
+    assert_close(mvd.cpu().numpy(), nmv, 1e-5, "moving_var" + tag)
