@@ -7,6 +7,7 @@ scripts rather than a package -- put `sph3d-gcn_b200/utils` on sys.path and
 
     tf_ops/            host mirrors of the reference's op wrappers (tf_ops/*/tf_*.py)
     utils/sph3gcn_util layer library with the reference's signatures (utils/sph3gcn_util.py)
+    io/                TFRecord / tf.train.Example codec and the S3DIS block pipeline, without TensorFlow
     models/            the reference's model call graphs (models/SPH3D_*.py) on that layer library
     csrc/              hand-written CUDA kernels + the C ABI (include/sph3d_b200.h)
     lib/               built libsph3d_b200.so (git-ignored)
@@ -18,8 +19,9 @@ from . import _lib                                     # noqa: F401
 from .tf_ops import tf_nnquery, tf_buildkernel, tf_conv3d, tf_sample, tf_pool3d, tf_unpool3d  # noqa: F401
 from .utils import sph3gcn_util                        # noqa: F401
 from . import models                                   # noqa: F401
+from . import io                                       # noqa: F401
 
 build = _build_mod.build
 library_path = _lib.library_path
 __all__ = ["tf_nnquery", "tf_buildkernel", "tf_conv3d", "tf_sample", "tf_pool3d", "tf_unpool3d",
-           "sph3gcn_util", "models", "build", "library_path"]
+           "sph3gcn_util", "models", "io", "build", "library_path"]

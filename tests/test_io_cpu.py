@@ -1,0 +1,204 @@
+"""TFRecord container, tf.train.Example codec and the S3DIS block pipeline without TensorFlow
+(sph3d-gcn_b200/io, utils/data_util.py).  Pins: CRC-32C test vectors of RFC 3720 B.4; the Example wire format against the
+protobuf runtime (dynamic descriptors restating tensorflow/core/example/{example,feature}.proto)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture()
+def tfr(pkg):
+    return pkg.io.tfrecord
+
+
+def test_crc32c_rfc3720_vectors(tfr):
+    assert tfr.crc32c(b"123456789") == 0xE3069283
+    assert tfr.crc32c(bytes(32)) == 0x8A9136AA
+    assert tfr.crc32c(b"\xff" * 32) == 0x62A8AB43
+    assert tfr.crc32c(bytes(range(32))) == 0x46DD794E
+    assert tfr.crc32c(bytes(range(31, -1, -1))) == 0x113FDB5C
+    assert tfr.crc32c(b"") == 0
+    rng = np.random.default_rng(0)
+
+    def bytewise(data):                                         # bit-at-a-time definition, reflected polynomial
+        c = 0xFFFFFFFF
+        for b in data:
+            c ^= b
+            for _ in range(8):
+                c = (c >> 1) ^ (0x82F63B78 if c & 1 else 0)
+        return c ^ 0xFFFFFFFF
+    for n in (1, 7, 8, 9, 15, 16, 17, 63, 64, 100, 1001):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert tfr.crc32c(data) == bytewise(data), n
+    a, b = b"hello ", b"world"
+    assert tfr.crc32c(b, tfr.crc32c(a)) == tfr.crc32c(a + b)    # incremental form
+    c = tfr.crc32c(b"abc")
+    assert tfr.masked_crc32c(b"abc") == ((((c >> 15) | (c << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def _example_messages():
+    """tensorflow/core/example/feature.proto + example.proto restated as dynamic protobuf descriptors"""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="sph3d_test_example.proto", package="sph3dtest", syntax="proto3")
+
+    def msg(name, *fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = tname
+        return m
+    msg("BytesList", ("value", 1, F.TYPE_BYTES, F.LABEL_REPEATED, None))
+    msg("FloatList", ("value", 1, F.TYPE_FLOAT, F.LABEL_REPEATED, None))
+    msg("Int64List", ("value", 1, F.TYPE_INT64, F.LABEL_REPEATED, None))
+    feat = msg("Feature", ("bytes_list", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".sph3dtest.BytesList"),
+               ("float_list", 2, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".sph3dtest.FloatList"),
+               ("int64_list", 3, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".sph3dtest.Int64List"))
+    feat.oneof_decl.add(name="kind")
+    for f in feat.field:
+        f.oneof_index = 0
+    feats = msg("Features", ("feature", 1, F.TYPE_MESSAGE, F.LABEL_REPEATED, ".sph3dtest.Features.FeatureEntry"))
+    entry = feats.nested_type.add(name="FeatureEntry")
+    entry.options.map_entry = True
+    entry.field.add(name="key", number=1, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    entry.field.add(name="value", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name=".sph3dtest.Feature")
+    msg("Example", ("features", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".sph3dtest.Features"))
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, "GetMessageClass", None)
+    if get is None:
+        factory = message_factory.MessageFactory(pool)
+        get = factory.GetPrototype
+    return get(pool.FindMessageTypeByName("sph3dtest.Example"))
+
+
+def test_example_codec_against_protobuf_runtime(tfr):
+    Example = _example_messages()
+    rng = np.random.default_rng(1)
+    xyz = rng.random((50, 3), dtype=np.float32)
+    seg = rng.integers(0, 13, 50).astype(np.int32)
+    ex = Example()
+    ex.features.feature["xyz_raw"].bytes_list.value.append(xyz.tobytes())
+    ex.features.feature["seg_label"].bytes_list.value.append(seg.tobytes())
+    ex.features.feature["scene_label"].int64_list.value.extend([7, -3, 1 << 40])
+    ex.features.feature["weights"].float_list.value.extend([0.5, -1.25, 3.0])
+    got = tfr.parse_example(ex.SerializeToString())            # written by protobuf, read by this codec
+    assert set(got) == {"xyz_raw", "seg_label", "scene_label", "weights"}
+    assert got["xyz_raw"] == [xyz.tobytes()] and got["seg_label"] == [seg.tobytes()]
+    assert got["scene_label"].tolist() == [7, -3, 1 << 40]
+    assert got["weights"].tolist() == [0.5, -1.25, 3.0]
+    mine = tfr.make_example({"xyz_raw": xyz.tobytes(), "seg_label": seg.tobytes(),
+                             "scene_label": np.array([7, -3, 1 << 40]), "weights": np.array([0.5, -1.25, 3.0], np.float32)})
+    back = Example()
+    back.ParseFromString(mine)                                  # written by this codec, read by protobuf
+    assert back.features.feature["xyz_raw"].bytes_list.value[0] == xyz.tobytes()
+    assert list(back.features.feature["scene_label"].int64_list.value) == [7, -3, 1 << 40]
+    assert list(back.features.feature["weights"].float_list.value) == [0.5, -1.25, 3.0]
+    assert back == ex
+
+
+def _block(rng, n):
+    xyz = rng.random((n, 3), dtype=np.float32) * 1.5
+    rgb = rng.random((n, 3), dtype=np.float32)
+    seg = rng.integers(0, 13, n).astype(np.int32)
+    inner = (rng.random(n) < 0.7).astype(np.int32)
+    return xyz, rgb, seg, inner
+
+
+def _record(tfr, xyz, rgb, seg, inner):
+    # the feature set of io/make_tfrecord_s3dis.py:233-241
+    return tfr.make_example({"rgb_raw": rgb.tobytes(), "seg_label": seg.tobytes(), "inner_label": inner.tobytes(),
+                             "index_label": np.arange(len(xyz), dtype=np.int32).tobytes(), "scene_label": np.array([3]),
+                             "scene_idx": np.array([11]), "rel_xyz_raw": (xyz / 2).tobytes(), "xyz_raw": xyz.tobytes()})
+
+
+def test_tfrecord_round_trip_and_corruption(tfr, tmp_path):
+    rng = np.random.default_rng(2)
+    blocks = [_block(rng, n) for n in (5, 40, 17)]
+    path = str(tmp_path / "Area_1.tfrecord")
+    tfr.write_records(path, [_record(tfr, *b) for b in blocks])
+    recs = list(tfr.read_records(path))
+    assert len(recs) == 3
+    f = tfr.parse_example(recs[1])
+    assert np.array_equal(np.frombuffer(f["xyz_raw"][0], "<f4").reshape(-1, 3), blocks[1][0])
+    assert f["scene_idx"].tolist() == [11]
+    raw = bytearray(open(path, "rb").read())
+    first_len, = struct.unpack("<Q", raw[:8])
+    assert struct.unpack("<I", raw[8:12])[0] == tfr.masked_crc32c(bytes(raw[:8]))
+    raw[12 + first_len // 2] ^= 0x40                            # flip a payload bit of record 0
+    bad = str(tmp_path / "bad.tfrecord")
+    open(bad, "wb").write(raw)
+    with pytest.raises(tfr.RecordError, match="payload"):
+        list(tfr.read_records(bad))
+    assert len(list(tfr.read_records(bad, check_crc=False))) == 3
+    open(bad, "wb").write(bytes(raw[:-3]))
+    with pytest.raises(tfr.RecordError, match="truncated"):
+        list(tfr.read_records(bad, check_crc=False))
+
+
+def test_s3dis_pipeline_semantics(pkg, tfr, tmp_path):
+    si = pkg.io.s3dis_input
+    rng = np.random.default_rng(3)
+    sizes = (30, 100, 64, 7, 55)
+    blocks = [_block(rng, n) for n in sizes]
+    path = str(tmp_path / "a.tfrecord")
+    tfr.write_records(path, [_record(tfr, *b) for b in blocks])
+    one = si.parse_fn(next(tfr.read_records(path)))             # train_s3dis.py:145-171
+    assert one.shape == (30, 8) and one.dtype == np.float32
+    assert np.array_equal(one[:, 0:3], blocks[0][0]) and np.array_equal(one[:, 3:6], blocks[0][1])
+    assert np.array_equal(one[:, 6], blocks[0][2].astype(np.float32)) and np.array_equal(one[:, 7], blocks[0][3].astype(np.float32))
+    batches = list(si.input_fn([path], batch_size=2, buffer_size=3, rng=np.random.default_rng(4)))
+    assert [b.shape[0] for b in batches] == [2, 2, 1]           # drop_remainder=False
+    seen = sorted(int((b[i, :, -1] >= 0).sum()) for b in batches for i in range(b.shape[0]))
+    assert seen == sorted(sizes)                                # every block once, padding = -1
+    for b in batches:
+        assert b.shape[2] == si.INPUT_DIM + 2 and (b[b[:, :, -1] < 0] == -1.0).all()
+    padded = si.padded_batch([si.parse_fn(r) for r in tfr.read_records(path)])
+    assert padded.shape == (5, 100, 8)
+    inp, lab, inner = si.select_points(padded, 64, rng=np.random.default_rng(5))   # :321-350
+    assert inp.shape == (5, 64, 6) and lab.shape == (5, 64) and inner.shape == (5, 64) and lab.dtype == np.int32
+    for i, (xyz, rgb, seg, inn) in enumerate(blocks):
+        rows = {tuple(r) for r in np.concatenate([xyz, rgb], 1).tolist()}
+        assert all(tuple(r) in rows for r in inp[i].tolist())    # only real points, never padding
+        n_unique = len({tuple(r) for r in inp[i].tolist()})
+        if len(xyz) >= 64:
+            assert n_unique == 64                               # without replacement when the block is large enough
+        else:
+            assert n_unique <= len(xyz)
+        assert set(lab[i].tolist()) <= set(seg.tolist()) and set(inner[i].tolist()) <= {0, 1}
+    a_in, a_lab, a_inner = si.augment_fn(inp.copy(), lab.copy(), inner.copy(), rng=np.random.default_rng(6))   # :113-142
+    assert a_in.shape == inp.shape and sorted(a_lab.sum(1).tolist()) == sorted(lab.sum(1).tolist())
+    assert np.allclose(np.sort(a_in[:, :, 3:6].sum((1, 2))), np.sort(inp[:, :, 3:6].sum((1, 2))), rtol=1e-5)   # rgb only permuted
+
+
+def test_augmentations(pkg):
+    du = pkg.utils.data_util
+    rng = np.random.default_rng(7)
+    pts = rng.standard_normal((6, 200, 3)).astype(np.float32)
+    rot = du.rotate_point_cloud(pts, rng=np.random.default_rng(8))
+    assert rot.dtype == np.float32 and np.allclose(rot[:, :, 2], pts[:, :, 2], atol=1e-6)          # about the up axis
+    assert np.allclose(np.linalg.norm(rot, axis=2), np.linalg.norm(pts, axis=2), atol=1e-5)
+    assert not np.allclose(rot, pts)
+    assert np.array_equal(rot, du.rotate_point_cloud(pts, rng=np.random.default_rng(8)))           # reproducible
+    quarter = du.rotate_point_cloud_by_angle(pts, np.pi / 2)                                        # p' = p Rz: (x, y) -> (y, -x)
+    assert np.allclose(quarter[:, :, 0], pts[:, :, 1], atol=1e-6) and np.allclose(quarter[:, :, 1], -pts[:, :, 0], atol=1e-6)
+    per = du.rotate_perturbation_point_cloud(pts, rng=np.random.default_rng(9))
+    assert np.allclose(np.linalg.norm(per, axis=2), np.linalg.norm(pts, axis=2), atol=1e-5)
+    cosang = (per * pts).sum(2) / np.maximum(np.linalg.norm(pts, axis=2) ** 2, 1e-12)
+    assert cosang.min() > np.cos(3 * 0.18 + 1e-3)                                                    # three clipped angles
+    jit = du.jitter_point_cloud(pts, rng=np.random.default_rng(10))
+    assert np.abs(jit - pts).max() <= 0.02 + 1e-7 and np.abs(jit - pts).std() > 0.005
+    sh = du.shift_point_cloud(pts, rng=np.random.default_rng(11))
+    d = sh - pts
+    assert np.allclose(d, d[:, :1, :], atol=1e-6) and np.abs(d).max() <= 0.1 + 1e-6
+    sc = du.random_scale_point_cloud(pts, rng=np.random.default_rng(12))
+    ratio = np.linalg.norm(sc, axis=2) / np.linalg.norm(pts, axis=2)
+    assert np.allclose(ratio, ratio[:, :1], rtol=1e-4) and 0.8 <= ratio.min() and ratio.max() <= 1.25
+    xn = np.concatenate([pts, pts / np.linalg.norm(pts, axis=2, keepdims=True)], axis=2)
+    rn = du.rotate_point_cloud_with_normal(xn, rng=np.random.default_rng(13))
+    assert np.allclose((rn[:, :, :3] * rn[:, :, 3:]).sum(2), (xn[:, :, :3] * xn[:, :, 3:]).sum(2), atol=1e-4)
+    data, labels, idx = du.shuffle_data(pts, np.arange(6), rng=np.random.default_rng(14))
+    assert np.array_equal(data, pts[idx]) and sorted(labels.tolist()) == list(range(6))
