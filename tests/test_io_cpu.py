@@ -202,3 +202,51 @@ def test_augmentations(pkg):
     assert np.allclose((rn[:, :, :3] * rn[:, :, 3:]).sum(2), (xn[:, :, :3] * xn[:, :, 3:]).sum(2), atol=1e-4)
     data, labels, idx = du.shuffle_data(pts, np.arange(6), rng=np.random.default_rng(14))
     assert np.array_equal(data, pts[idx]) and sorted(labels.tolist()) == list(range(6))
+
+
+def test_block_overlap_evaluation(pkg):
+    """evaluate_s3dis_with_overlap.py:245-318: resample until every inner point is covered, sum logits per point, score inner points"""
+    ev, si = pkg.io.s3dis_eval, pkg.io.s3dis_input
+    rng = np.random.default_rng(21)
+    sizes, num_point, ncls = (300, 90, 150), 128, 5
+    items = []
+    for n in sizes:
+        xyz, rgb = rng.random((n, 3), dtype=np.float32), rng.random((n, 3), dtype=np.float32)
+        seg = rng.integers(0, ncls, n).astype(np.float32)
+        inner = (rng.random(n) < 0.6).astype(np.float32)
+        items.append(np.concatenate([xyz, rgb, seg[:, None], inner[:, None]], axis=1))
+    padded = si.padded_batch(items)
+    assert ev.block_lengths(padded).tolist() == list(sizes)
+    lookup = {tuple(np.round(row[:6], 6).tolist()): int(row[6]) for it in items for row in it}
+    calls = []
+
+    def oracle_net(batch_input):                                # a "network" that knows the label of every point
+        calls.append(batch_input.shape)
+        out = np.zeros(batch_input.shape[:2] + (ncls,), dtype=np.float32)
+        for b in range(batch_input.shape[0]):
+            for j in range(batch_input.shape[1]):
+                out[b, j, lookup[tuple(np.round(batch_input[b, j], 6).tolist())]] = 1.0
+        return out
+
+    summed, counts, rounds = ev.predict_blocks_with_overlap(padded, num_point, oracle_net, ncls, rng=np.random.default_rng(22))
+    assert rounds == len(calls) >= 3 and all(c == (3, num_point, 6) for c in calls)   # 300 points need several draws of 128
+    metrics = ev.SegmentationMetrics(ncls)
+    for i, it in enumerate(items):
+        inner = it[:, 7] == 1
+        assert (counts[i][inner] > 0).all()                     # stop criterion: every inner point drawn at least once
+        assert counts[i].sum() == rounds * num_point
+        drawn = counts[i] > 0
+        assert (summed[i][~drawn] == 0).all() and (summed[i][drawn].sum(1) > 0).all()
+        metrics.update(summed[i], it[:, 6], it[:, 7])
+    res = metrics.result()
+    assert res["accuracy"] == 1.0 and np.allclose(res["iou"], 1.0) and res["mean_iou"] == 1.0
+    wrong = ev.SegmentationMetrics(ncls)                         # everything predicted as class 0
+    for i, it in enumerate(items):
+        z = np.zeros_like(summed[i]); z[:, 0] = 1
+        wrong.update(z, it[:, 6], it[:, 7])
+    r = wrong.result()
+    inner_gt = np.concatenate([it[it[:, 7] == 1, 6] for it in items])
+    assert np.isclose(r["accuracy"], (inner_gt == 0).mean()) and np.isclose(r["iou"][0], (inner_gt == 0).mean())
+    assert (r["iou"][1:] == 0).all()
+    with pytest.raises(ValueError):
+        ev.predict_blocks_with_overlap(padded, num_point, lambda x: np.zeros((3, num_point, ncls + 1)), ncls)
