@@ -38,25 +38,8 @@ def padded_batch(items, pad_value=-1.0):
 def input_fn(filelist, batch_size=16, buffer_size=10000, rng=None, check_crc=True):
     """Generator of padded batches over all records of `filelist`, shuffled through a `buffer_size` reservoir like
     tf.data.Dataset.shuffle; the last batch may be smaller (drop_remainder=False)."""
-    rng = np.random.default_rng() if rng is None else rng
-
-    def shuffled():
-        buf = []
-        for path in filelist:
-            for rec in tfrecord.read_records(path, check_crc=check_crc):
-                buf.append(rec)
-                if len(buf) > buffer_size:
-                    yield buf.pop(int(rng.integers(len(buf))))
-        while buf:
-            yield buf.pop(int(rng.integers(len(buf))))
-
-    batch = []
-    for rec in shuffled():
-        batch.append(parse_fn(rec))
-        if len(batch) == batch_size:
-            yield padded_batch(batch)
-            batch = []
-    if batch:
+    records = tfrecord.shuffled_records(filelist, buffer_size, rng, check_crc)
+    for batch in tfrecord.batched((parse_fn(rec) for rec in records), batch_size):
         yield padded_batch(batch)
 
 

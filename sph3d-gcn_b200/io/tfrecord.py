@@ -224,3 +224,30 @@ def make_example(features):
                 feat = _ld(3, _ld(1, b"".join(_enc_varint(int(x)) for x in arr.reshape(-1))))
         entries += _ld(1, _ld(1, key.encode("utf-8")) + _ld(2, feat))
     return _ld(1, entries)
+
+
+# ---------------------------------------------------------------------------------------------- dataset plumbing
+def shuffled_records(filelist, buffer_size=10000, rng=None, check_crc=True):
+    """tf.data.TFRecordDataset(filelist).shuffle(buffer_size): records pass through a reservoir of `buffer_size`
+    entries from which one is drawn uniformly each time a new one arrives."""
+    rng = np.random.default_rng() if rng is None else rng
+    buf = []
+    for path in filelist:
+        for rec in read_records(path, check_crc=check_crc):
+            buf.append(rec)
+            if len(buf) > buffer_size:
+                yield buf.pop(int(rng.integers(len(buf))))
+    while buf:
+        yield buf.pop(int(rng.integers(len(buf))))
+
+
+def batched(items, batch_size):
+    """lists of up to batch_size consecutive items (drop_remainder=False)"""
+    batch = []
+    for it in items:
+        batch.append(it)
+        if len(batch) == batch_size:
+            yield batch
+            batch = []
+    if batch:
+        yield batch

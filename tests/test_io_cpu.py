@@ -250,3 +250,28 @@ def test_block_overlap_evaluation(pkg):
     assert (r["iou"][1:] == 0).all()
     with pytest.raises(ValueError):
         ev.predict_blocks_with_overlap(padded, num_point, lambda x: np.zeros((3, num_point, ncls + 1)), ncls)
+
+
+def test_shapenet_and_modelnet_records(pkg, tfr, tmp_path):
+    rng = np.random.default_rng(41)
+    shapes = [(rng.random((n, 3), dtype=np.float32), rng.integers(0, 50, n).astype(np.int32)) for n in (20, 35, 28)]
+    p1 = str(tmp_path / "shapenet.tfrecord")
+    tfr.write_records(p1, [tfr.make_example({"xyz_raw": x.tobytes(), "part_label": l.tobytes()}) for x, l in shapes])
+    sn = pkg.io.shapenet_input
+    batches = list(sn.input_fn([p1], batch_size=2, buffer_size=2, rng=np.random.default_rng(1)))      # train_shapenet.py:155-180
+    assert [b.shape for b in batches] in ([(2, 35, 4), (1, 20, 4)], [(2, 35, 4), (1, 28, 4)], [(2, 28, 4), (1, 35, 4)])
+    rows = np.concatenate([b[i][b[i, :, -1] >= 0] for b in batches for i in range(len(b))])
+    want = np.concatenate([np.concatenate([x, l[:, None].astype(np.float32)], 1) for x, l in shapes])
+    assert sorted(map(tuple, rows.tolist())) == sorted(map(tuple, want.tolist()))
+    clouds = [(rng.random((64, 3), dtype=np.float32), int(rng.integers(0, 40))) for _ in range(5)]
+    p2 = str(tmp_path / "modelnet.tfrecord")
+    tfr.write_records(p2, [tfr.make_example({"xyz_raw": x.tobytes(), "label": np.array([l])}) for x, l in clouds])
+    mn = pkg.io.modelnet_input
+    got = list(mn.input_fn([p2], batch_size=2, buffer_size=10, rng=np.random.default_rng(2)))          # train_modelnet.py:118-138
+    assert [x.shape for x, _ in got] == [(2, 64, 3), (2, 64, 3), (1, 64, 3)] and got[0][1].dtype == np.int32
+    assert sorted(int(l) for _, ls in got for l in ls) == sorted(l for _, l in clouds)
+    by_label = {l: x for x, l in clouds}
+    for xs, ls in got:
+        for x, l in zip(xs, ls):
+            if sum(1 for _, l2 in clouds if l2 == int(l)) == 1:
+                assert np.array_equal(x, by_label[int(l)])
