@@ -6,6 +6,8 @@
                              block holds fewer), split into input / label / inner mask
   augment_fn      :113-142   shuffle clouds and point order; first third of the batch rotated about z + perturbed,
                              second third jittered
+ScanNet blocks carry the same features and the same pipeline (scannet_seg/train_scannet.py:130-160, INPUT_DIM = 6;
+io/make_tfrecord_scannet.py:188-194), so this module reads them too.
 The arrays `select_points` returns are what the model call graph consumes (models/SPH3D_s3dis.get_model / get_loss).
 """
 import numpy as np
