@@ -27,12 +27,16 @@
 extern "C" {
 #endif
 
-#define SPH3D_B200_ABI_VERSION 2
+#define SPH3D_B200_ABI_VERSION 3
 int sph3d_abi_version(void);
 
 /* Number of KERNELS (memsets excluded) the calling thread's most recent entry-point call enqueued (bench.py
  * gpu_launches).  The counter is thread-local: every entry point is reentrant. */
 int sph3d_last_launch_count(void);
+
+/* The SPH3D_* launch tunables are read from the environment once, when the library is loaded.
+ * A process that changes one afterwards (sweep scripts, tests) calls this to re-read them. */
+void sph3d_reload_tunables(void);
 
 /* ---- a1: buildSphereNeighborLauncher, tf_nnquery_gpu.cu:115-121 (kernel :15-65) --------------
  * Ball query with the reference's growing-radius chain semantics: bit-exact
@@ -65,10 +69,30 @@ int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, int K,
                            const int* nn_index, const int* nn_count, const int* bin_index,
                            const float* input, const float* filter, float* output, void* stream);
 
+/* ---- a4, split form: the same launcher with its graph-only work hoisted out ---------------------------------
+ * sph3d_depthwise_conv3d groups every 64-edge tile of a row by filter bin before it gathers (so that the filter is
+ * applied once per (row, bin) instead of once per edge).  That grouping depends only on (nn_index, nn_count,
+ * bin_index, F): sph3d_conv_sort writes it once per graph -- (B,M,K) words, neighbour id << 8 | bin << 1 | last --
+ * and sph3d_depthwise_conv3d_planned convolves from those words; outputs are bit-identical to the one-call form.
+ * The reference's models apply two convolutions per graph (models/SPH3D_*.py call separable_conv3d twice per level);
+ * the graph-build side (tf_buildkernel.spherical_kernel in the Python layer) emits the words next to filt_index.
+ * sph3d_conv_sort_bytes returns 0 where the planned form does not apply (F > 128, N >= 2^24);
+ * sph3d_depthwise_conv3d_planned_supported returns 0 when (C, r) is not covered (r > 2). */
+size_t sph3d_conv_sort_bytes(int B, int N, int M, int F, int K);
+int sph3d_conv_sort(int B, int N, int M, int F, int K,
+                    const int* nn_index, const int* nn_count, const int* bin_index,
+                    void* plan, size_t plan_bytes, void* stream);
+size_t sph3d_depthwise_conv3d_planned_supported(int B, int N, int M, int F, int C, int r, int K);
+int sph3d_depthwise_conv3d_planned(int B, int N, int M, int F, int C, int r, int K,
+                                   const int* nn_count, const void* plan, size_t plan_bytes,
+                                   const float* input, const float* filter, float* output, void* stream);
+
 /* ---- a5: depthwiseConv3dGradLauncher, tf_conv3d_gpu.cu:115-140 (kernels :32-101) -------------
  * workspace: sph3d_depthwise_conv3d_grad_workspace_bytes(...) bytes of device scratch (transposed graph,
- * scaled grad_output, per-CTA filter-gradient partials reduced in a fixed order => grad_filter is
- * deterministic run to run). */
+ * per-CTA filter-gradient partials reduced in a fixed order).  Summation order: the row-owned form (r = 2 one-call,
+ * F > 130) is run-to-run deterministic in grad_filter; the transposed form orders the edges of a segment by an
+ * atomic rank, so grad_input / grad_filter may differ in the last ulps between runs (as the reference's atomics
+ * do) unless SPH3D_BWDT_SORT=1 asks for the canonical (ascending output point) order. */
 size_t sph3d_depthwise_conv3d_grad_workspace_bytes(int B, int N, int M, int F, int C, int r, int K);
 int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, int r, int K,
                                 const int* nn_index, const int* nn_count, const int* bin_index,
@@ -82,7 +106,10 @@ int sph3d_depthwise_conv3d_grad(int B, int N, int M, int F, int C, int r, int K,
  * (nn_index, nn_count, bin_index, F); a caller that applies several convolutions over one graph (the reference's
  * models run two per level: sph3gcn_util.py:88-161 called twice per level in models/SPH3D_*.py) or
  * steps a static graph builds it once with sph3d_conv_transpose and passes it to ..._grad_planned.
- * sph3d_conv_transpose_bytes returns 0 when the planned form does not apply (F > 72, M >= 2^24);
+ * The plan entry of an edge carries nn_count of its output row when the bits allow (B*M*K*slots <= 2^32), so the gather
+ * pass scales by 1/cnt itself and reads grad_output directly (no scaled copy).
+ * sph3d_conv_transpose_bytes returns 0 when the planned form does not apply (more than 127 bins per warp class or
+ * accumulators beyond shared memory: F > ~380; B*M*slots > 2^32);
  * sph3d_depthwise_conv3d_grad_planned_workspace_bytes returns 0 when (C, r) is not covered (r > 2). */
 size_t sph3d_conv_transpose_bytes(int B, int N, int M, int F, int K);
 int sph3d_conv_transpose(int B, int N, int M, int F, int K,
@@ -111,17 +138,25 @@ int sph3d_max_pool3d_grad(int B, int N, int M, int C, const int* max_index,
 /* ---- a9: avgPool3dLauncher / avgPool3dGradLauncher, tf_pool3d_gpu.cu:107-119 ----------------- */
 int sph3d_avg_pool3d(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
                      const float* input, float* output, void* stream);
+/* Gradient, two forms.  With workspace == NULL the neighbour rows scatter into grad_input with vector reductions (one
+ * per edge).  With sph3d_avg_pool3d_grad_workspace_bytes(...) bytes of scratch (0 = shape not covered) the graph is
+ * transposed first and every input point GATHERS the rows that reference it: no atomics, no zero fill. */
+size_t sph3d_avg_pool3d_grad_workspace_bytes(int B, int N, int M, int C, int K);
 int sph3d_avg_pool3d_grad(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
-                          const float* grad_output, float* grad_input, void* stream);
+                          const float* grad_output, float* grad_input,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a10: meanInterpolateLauncher / GradLauncher, tf_unpool3d_gpu.cu:87-99 -------------------
  * As in the reference, N = fine (output) points, M = coarse (input) points:
  * input (B,M,C), nn_index (B,N,K) into the coarse cloud, output (B,N,C). */
 int sph3d_mean_interpolate(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
                            const float* input, float* output, void* stream);
+/* gradients: scatter form (workspace == NULL) or gather form over the transposed graph, as for avg-pool;
+ * sph3d_interpolate_grad_workspace_bytes serves both the mean and the weighted gradient. */
+size_t sph3d_interpolate_grad_workspace_bytes(int B, int N, int M, int C, int K);
 int sph3d_mean_interpolate_grad(int B, int N, int M, int C, int K, const int* nn_index,
                                 const int* nn_count, const float* grad_output, float* grad_input,
-                                void* stream);
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a11: weightedInterpolateLauncher / GradLauncher, tf_unpool3d_gpu.cu:101-113 ------------- */
 int sph3d_weighted_interpolate(int B, int N, int M, int C, int K, const int* nn_index,
@@ -129,7 +164,7 @@ int sph3d_weighted_interpolate(int B, int N, int M, int C, int K, const int* nn_
                                float* output, void* stream);
 int sph3d_weighted_interpolate_grad(int B, int N, int M, int C, int K, const int* nn_index,
                                     const int* nn_count, const float* grad_output, const float* weight,
-                                    float* grad_input, void* stream);
+                                    float* grad_input, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a12 (layer tail): bias -> activation -> batch normalisation, utils/sph3gcn_util.py:147-161, :206-220, :257-271
  * (tf.nn.bias_add, activation_fn = tf.nn.elu, tf.layers.batch_normalization(momentum=0.99) at :328-332).  The reference

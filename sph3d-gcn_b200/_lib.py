@@ -22,6 +22,11 @@ _P = c_void_p
 SIGNATURES = {
     "sph3d_abi_version": (c_int, []),
     "sph3d_last_launch_count": (c_int, []),
+    "sph3d_reload_tunables": (None, []),
+    "sph3d_conv_sort_bytes": (c_size_t, [c_int] * 5),
+    "sph3d_conv_sort": (c_int, [c_int] * 5 + [_P] * 4 + [c_size_t, _P]),
+    "sph3d_depthwise_conv3d_planned_supported": (c_size_t, [c_int] * 7),
+    "sph3d_depthwise_conv3d_planned": (c_int, [c_int] * 7 + [_P, _P, c_size_t] + [_P] * 4),
     "sph3d_build_sphere_neighbor_workspace_bytes": (c_size_t, [c_int] * 4),
     "sph3d_build_sphere_neighbor": (c_int, [c_int] * 4 + [c_float] + [_P] * 6 + [c_size_t, _P]),
     "sph3d_build_cube_neighbor": (c_int, [c_int] * 5 + [c_float] + [_P] * 5),
@@ -38,11 +43,13 @@ SIGNATURES = {
     "sph3d_max_pool3d": (c_int, [c_int] * 5 + [_P] * 6),
     "sph3d_max_pool3d_grad": (c_int, [c_int] * 4 + [_P] * 4),
     "sph3d_avg_pool3d": (c_int, [c_int] * 5 + [_P] * 5),
-    "sph3d_avg_pool3d_grad": (c_int, [c_int] * 5 + [_P] * 5),
+    "sph3d_avg_pool3d_grad_workspace_bytes": (c_size_t, [c_int] * 5),
+    "sph3d_avg_pool3d_grad": (c_int, [c_int] * 5 + [_P] * 5 + [c_size_t, _P]),
     "sph3d_mean_interpolate": (c_int, [c_int] * 5 + [_P] * 5),
-    "sph3d_mean_interpolate_grad": (c_int, [c_int] * 5 + [_P] * 5),
+    "sph3d_interpolate_grad_workspace_bytes": (c_size_t, [c_int] * 5),
+    "sph3d_mean_interpolate_grad": (c_int, [c_int] * 5 + [_P] * 5 + [c_size_t, _P]),
     "sph3d_weighted_interpolate": (c_int, [c_int] * 5 + [_P] * 6),
-    "sph3d_weighted_interpolate_grad": (c_int, [c_int] * 5 + [_P] * 6),
+    "sph3d_weighted_interpolate_grad": (c_int, [c_int] * 5 + [_P] * 6 + [c_size_t, _P]),
     "sph3d_bias_act_bn_workspace_bytes": (c_size_t, [c_int] * 2),
     "sph3d_bias_act_bn": (c_int, [c_int] * 4 + [c_float] * 2 + [_P] * 10 + [c_size_t, _P]),
     "sph3d_bias_act_bn_grad": (c_int, [c_int] * 4 + [_P] * 11 + [c_size_t, _P]),
@@ -69,15 +76,24 @@ def lib():
                 raise ImportError(
                     "sph3d-gcn_b200: %s is missing and could not be built (%s). There is no CPU "
                     "fallback: build it with `python sph3d-gcn_b200/build.py`." % (path, e))
+            if os.environ.get("SPH3D_ALLOW_STALE_LIB") != "1":
+                import warnings
+                warnings.warn("sph3d-gcn_b200: %s is older than its sources and the rebuild failed (%s); loading the "
+                              "stale binary. Set SPH3D_ALLOW_STALE_LIB=1 to silence." % (path, e), RuntimeWarning)
     handle = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)      # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if handle.sph3d_abi_version() != 2:
+    if handle.sph3d_abi_version() != 3:
         raise ImportError("sph3d-gcn_b200: ABI version mismatch in %s" % path)
     _LIB = handle
     return _LIB
+
+
+def reload_tunables():
+    """re-read the SPH3D_* environment variables (the library reads them once, at load)"""
+    lib().sph3d_reload_tunables()
 
 
 def stream_ptr():

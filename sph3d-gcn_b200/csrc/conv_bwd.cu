@@ -250,12 +250,12 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 136) return p;
     int vec = pick_vec_full_warp(C), slots = 0, G = 0;
     {   // sweep knob: force a strip width (must divide C)
-        int v_env = tune_int("SPH3D_BWD_VEC", vec);
+        int v_env = tun(tunables().bwd_vec, vec);
         if ((v_env == 1 || v_env == 2 || v_env == 4) && C % v_env == 0) vec = v_env;
     }
     // narrow strips (vec <= 2: C <= 64) keep few accumulators per bin: 9 bins per warp (4 warps per row) then fit in
     // <= 36 registers and 24 warps per SM, which measured faster than 17 bins per warp (0.38 vs 0.48 ms, C=64, r=2)
-    if (vec <= 2 && 9 * vec * r <= 36 && 4 * 9 >= F && tune_int("SPH3D_BWD_G", 4) == 4) { G = 4; slots = 9; }
+    if (vec <= 2 && 9 * vec * r <= 36 && 4 * 9 >= F && tun(tunables().bwd_g, 4) == 4) { G = 4; slots = 9; }
     for (; vec >= 1 && !G; vec = (vec > 1 ? vec >> 1 : 0)) {
         const int slot_opts[2] = {17, 9};
         for (int i = 0; i < 2 && !G; i++) {
@@ -268,7 +268,7 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     }
     if (!G) return p;
     {   // sweep knob: a larger group (fewer bins per warp) is always legal
-        int g_env = tune_int("SPH3D_BWD_G", G);
+        int g_env = tun(tunables().bwd_g, G);
         if ((g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) && g_env > G) G = g_env;
         if (G * 9 >= F) slots = 9;                      // fewer bins per warp -> fewer registers -> more warps
     }
@@ -277,7 +277,7 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     p.vec = vec; p.slots = slots; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
     const int max_threads = bwd_max_threads(vec, r, slots) / (32 * G) * (32 * G);
-    p.threads = tune_int("SPH3D_BWD_THREADS", max_threads);
+    p.threads = tun(tunables().bwd_threads, max_threads);
     if (p.threads > max_threads || p.threads % (32 * G)) p.threads = max_threads;
     const long long rows = (long long)B * M;
     long long want = sm_count();
@@ -288,14 +288,20 @@ static ConvPlan plan_bwd(int B, int N, int M, int F, int C, int r, int* G_out)
     p.rpc = rpc;
     const long long nchunks = (rows + rpc - 1) / rpc;
     p.grid_x = (int)(nchunks < want ? nchunks : want);
-    while (p.threads > 32 * G && p.threads > 64 &&
-           (long long)p.grid_x * p.chunks * (p.threads / (32 * G)) > rows && p.grid_x * p.chunks < sm_count())
-        p.threads >>= 1;
+    // tiny problems: fewer warp GROUPS per CTA (a CTA must stay a whole number of G-warp groups: a partial group would
+    // re-process a row with some of its bins and write its partial past the end of the workspace)
+    {
+        int groups = p.threads / (32 * G);
+        while (groups > 1 && groups * 32 * G > 64 &&
+               (long long)p.grid_x * p.chunks * groups > rows && p.grid_x * p.chunks < sm_count())
+            groups = (groups + 1) / 2;
+        p.threads = groups * 32 * G;
+    }
     {   // Summing the CTA's groups in shared memory (one partial per CTA) is OFF by default: the 8 extra
         // filter-sized slabs move the L1/shared carve-out from ~200 KB of L1 to ~76 KB and the gathers
         // lose more (2.27 -> 2.42 ms at Cfg-T) than the smaller second-stage reduction saves.
         const size_t need = smem * (1 + (size_t)(p.threads / 32 / G));
-        if (need <= SMEM_CAP && tune_int("SPH3D_BWD_CTA_REDUCE", 2) == 1) { p.cta_reduce = 1; p.smem = need; }
+        if (need <= SMEM_CAP && tunables().bwd_cta_reduce == 1) { p.cta_reduce = 1; p.smem = need; }
     }
     *G_out = G;
     return p;

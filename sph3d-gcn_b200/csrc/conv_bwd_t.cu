@@ -44,12 +44,12 @@ namespace sph3d {
 // SPH3D_BWDT_THREADS = 512 / 640 / 1024 and SPH3D_BWDT_DEPTH select the other compiled shapes (sweeps in profiles/)
 static inline int t_warps()
 {
-    const int t = tune_int("SPH3D_BWDT_THREADS", 768);
+    const int t = tun(tunables().bwdt_threads, 768);
     return (t == 512 || t == 640 || t == 1024) ? t / 32 : 24;
 }
 static inline int t_depth(int warps)
 {
-    const int d = tune_int("SPH3D_BWDT_DEPTH", 0);
+    const int d = tunables().bwdt_depth;
     if (warps == 16) return d == 4 ? 4 : 3;
     if (warps == 20) return d == 3 ? 3 : 2;
     if (warps == 32) return 1;
@@ -62,6 +62,8 @@ struct TGeom {
     int G, SLOTS, FP;           // bin classes (f % G), bins per class, G*SLOTS segments per point
     size_t nseg, nseg_pad;      // B*N*FP; nseg+1 (the total sits behind the last start) rounded up to SCAN_TILE
     int rank_bytes;             // 2 or 4: width of the per-edge rank scratch
+    int sb, cb;                 // entry = row << (sb+cb) | (cnt-1) << sb | slot: bits of the slot and of the folded 1/cnt code
+    bool fold;                  // cb > 0: the entry carries nn_count of its output row, the kernel gathers grad_output itself
     int scan_blocks;
     size_t seg_off, sums_off, ent_off, rank_off, total;   // byte offsets inside the plan
     bool ok;
@@ -79,7 +81,7 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
     // memory beside the filter and the staging arrays: F=33 -> G=4 x 9 bins, F=17 -> 2 x 9, F=49 -> 4 x 13
     int G = 0, SL = 0;
     const int nw = t_warps();
-    const int g_min = tune_int("SPH3D_BWDT_G", 1);
+    const int g_min = tun(tunables().bwdt_g, 1);
     // Bin 0 (the query point itself) holds one edge per point; the other F-1 bins split evenly over the classes
     // when G divides F-1 (n*p*q with n = 8 azimuth bins: G = 2, 4, 8), which keeps the classes' edge counts equal.
     for (int pass = 0; pass < 2 && !G; pass++)
@@ -88,10 +90,21 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
             if (pass == 0 && F > 1 && (F - 1) % d) continue;
             const int sl = (F + d - 1) / d;
             if (sl > 127) continue;
-            if ((size_t)nw * sl * 512 + (size_t)F * 512 + (size_t)nw * 512 <= 210 * 1024) { G = d; SL = sl; break; }
+            if ((size_t)nw * sl * 512 + (size_t)F * 512 + (size_t)nw * 768 <= 210 * 1024) { G = d; SL = sl; break; }
         }
     if (!G) return g;                                             // very large F: conv_bwd.cu handles it
-    if ((long long)B * M >= (1LL << 24)) return g;                // the output row b*M+m is packed into 24 bits
+    // entry layout: the slot (bin inside its class) in the low sb bits; above it, when they fit beside the output row
+    // b*M+m, the cb bits of nn_count-1 of that row, so that the gather kernel scales by 1/cnt itself and no scaled copy
+    // of grad_output is ever written (fold).  Otherwise cb = 0 and the kernel gathers a pre-scaled copy.
+    int sb = 1;
+    while ((1 << sb) < SL) sb++;
+    int cb = 1;
+    while ((1 << cb) < K) cb++;
+    const long long BM = (long long)B * M;
+    bool fold = BM <= (1LL << (32 - sb - cb));
+    if (!fold) cb = 0;
+    if (BM > (1LL << (32 - sb))) return g;
+    g.sb = sb; g.cb = cb; g.fold = fold;
     if ((long long)B * M * K >= (1LL << 31) || (long long)B * N * G * SL >= (1LL << 31)) return g;
     g.G = G; g.SLOTS = SL; g.FP = G * SL;
     g.nseg = (size_t)B * N * g.FP;
@@ -112,9 +125,11 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
 // one thread per edge slot (b,m,k); edges beyond nn_count and malformed ids are skipped.
 // Pass 1 (FILL = false): rank of the edge inside its segment from ONE returning integer atomic; seg ends up holding the
 // segment sizes.  Pass 2 (FILL = true, after the exclusive scan): position = start + rank, no atomics.
+// code_k: the cb code bits of an entry hold the edge's slot k in its row (weighted interpolation: the kernel fetches
+// weight[row, k]) instead of nn_count - 1.
 template <bool FILL, typename RankT>
 __global__ void __launch_bounds__(256)
-transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G, int SLOTS,
+transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G, int SLOTS, int sb, int cb, int code_k,
                        const int* __restrict__ nn_index, const int* __restrict__ nn_count,
                        const int* __restrict__ bin_index, int* __restrict__ seg, RankT* __restrict__ ranks,
                        unsigned* __restrict__ entries)
@@ -122,14 +137,16 @@ transpose_edges_kernel(size_t slots, unsigned M, unsigned N, int K, int F, int G
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x) {
         const size_t row = t / (unsigned)K;
         const int k = (int)(t - row * (unsigned)K);
-        if (k >= __ldg(nn_count + row)) continue;
-        const int n = __ldg(nn_index + t), f = __ldg(bin_index + t);
+        const int cnt = min(__ldg(nn_count + row), K);
+        if (k >= cnt) continue;
+        const int n = __ldg(nn_index + t), f = bin_index ? __ldg(bin_index + t) : 0;
         if ((unsigned)n >= N || (unsigned)f >= (unsigned)F) continue;
         const unsigned b = (unsigned)(row / M);
         const size_t s = ((size_t)b * N + n) * (G * SLOTS) + (f % G) * SLOTS + f / G;
         if constexpr (FILL) {
             const int pos = __ldg(seg + s) + (int)ranks[t];
-            entries[pos] = ((unsigned)row << 8) | (unsigned)(f / G);     // row = b*M + m: the row of gs this edge gathers
+            // row = b*M + m: the row of grad_output this edge gathers; cb bits of cnt-1 when the 1/cnt scale is folded in
+            entries[pos] = ((unsigned)row << (sb + cb)) | (cb ? ((unsigned)(code_k ? k : cnt - 1) << sb) : 0u) | (unsigned)(f / G);
         } else {
             ranks[t] = (RankT)atomicAdd(seg + s, 1);
         }
@@ -293,7 +310,7 @@ __device__ __forceinline__ void st_strip_smem(float* p, const float (&v)[VEC])
 // list + input strip (i+1), gathers (i); inside a point 4*DEPTH feature-strip gathers are in flight.
 template <int VEC, int R, int THREADS, int DEPTH>
 __global__ void __launch_bounds__(THREADS, 1)
-conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of gs */, int F, int C, int G, int SLOTS,
+conv_bwd_t_kernel(unsigned rows /* B*N */, int sb, int cb, int F, int C, int G, int SLOTS,
                   const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
                   const float* __restrict__ input, const float* __restrict__ filter,
                   float* __restrict__ grad_input, float* __restrict__ gw_partial)
@@ -313,8 +330,9 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
         Wsh[t] = (ch < Co) ? __ldg(filter + (size_t)f * Co + ch) : 0.f;
     }
     float* accS = Wsh + (size_t)F * STRIP + (size_t)warp * SLOTS * STRIP + lane * VEC;   // my accumulators [SLOTS][strip]
-    unsigned* sOff = reinterpret_cast<unsigned*>(Wsh + (size_t)F * STRIP + (size_t)NWARPS * SLOTS * STRIP) + warp * 128;
+    unsigned* sOff = reinterpret_cast<unsigned*>(Wsh + (size_t)F * STRIP + (size_t)NWARPS * SLOTS * STRIP) + warp * 192;
     int* sCode = reinterpret_cast<int*>(sOff + 64);
+    float* sScale = reinterpret_cast<float*>(sOff + 128);   // 1/cnt of the edge's output row (1 when gs is pre-scaled, 0 for padding)
     {
         float z[VEC];
 #pragma unroll
@@ -327,7 +345,8 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
     const bool active = i0 < Co;
     const int i0ld = active ? i0 : 0;                    // idle lanes load a valid strip, never store
     const unsigned gsStrideB = (unsigned)Co * 4u;
-    const unsigned zoff = zrow * gsStrideB;              // padding edges gather the zero row
+    const unsigned smask = (1u << sb) - 1u, cmask = (1u << cb) - 1u;
+    const int sh = sb + cb;
     const char* gb = reinterpret_cast<const char*>(gs) + (size_t)i0ld * 4;
     const float* inl = input + i0ld / R;                 // my first input channel
     float* gil = grad_input + i0ld / R;
@@ -383,8 +402,11 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
 #pragma unroll
         for (int e = 0; e < VEC; e++) { gi[e] = 0.f; T[e] = 0.f; }
 
-        auto consume = [&](const float (&v)[VEC], int code) {
-            strip_add<VEC>(T, v);
+        auto consume = [&](const float (&v)[VEC], int code, float sc) {
+            float scv[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) scv[e] = sc;
+            strip_fma<VEC>(T, v, scv);
             if (code & 1) {                                // last edge of its bin segment (warp-uniform)
                 const int s = code >> 1;
                 float w[VEC], a[VEC];
@@ -404,14 +426,15 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
         };
         auto consume4 = [&](int p, const float (&v)[4][VEC]) {
             const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
+            const float4 ss = *reinterpret_cast<const float4*>(sScale + p);
             if (((cc.x | cc.y | cc.z | cc.w) & 1) == 0) {  // no segment ends inside this batch (the common case)
-                float u[VEC], w2[VEC];
+                float s0[VEC], s1[VEC], s2[VEC], s3[VEC];
 #pragma unroll
-                for (int e = 0; e < VEC; e++) { u[e] = v[0][e]; w2[e] = v[2][e]; }
-                strip_add<VEC>(u, v[1]); strip_add<VEC>(w2, v[3]);
-                strip_add<VEC>(T, u); strip_add<VEC>(T, w2);
+                for (int e = 0; e < VEC; e++) { s0[e] = ss.x; s1[e] = ss.y; s2[e] = ss.z; s3[e] = ss.w; }
+                strip_fma<VEC>(T, v[0], s0); strip_fma<VEC>(T, v[1], s1);
+                strip_fma<VEC>(T, v[2], s2); strip_fma<VEC>(T, v[3], s3);
             } else {
-                consume(v[0], cc.x); consume(v[1], cc.y); consume(v[2], cc.z); consume(v[3], cc.w);
+                consume(v[0], cc.x, ss.x); consume(v[1], cc.y, ss.y); consume(v[2], cc.z, ss.z); consume(v[3], cc.w, ss.w);
             }
         };
 
@@ -425,20 +448,24 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow /* B*M: the zero row of
                 if (p0 < nt) e0 = __ldg(entries + kt + p0);
                 if (p1 < nt) e1 = __ldg(entries + kt + p1);
             }
-            const int s0 = (int)(e0 & 255u), s1 = (int)(e1 & 255u);
+            const int s0 = (int)(e0 & smask), s1 = (int)(e1 & smask);
+            // padding edges (tiles are rounded up to a multiple of four) gather the tile's first row with scale 0
+            const unsigned off_first = __shfl_sync(FULL_MASK, (e0 >> sh) * gsStrideB, 0);
             int nx0 = __shfl_down_sync(FULL_MASK, s0, 1);
             const int nx1 = __shfl_down_sync(FULL_MASK, s1, 1);
             const int first1 = __shfl_sync(FULL_MASK, s1, 0);
             if (lane == 31) nx0 = first1;
             if (p0 < nt4) {
                 const bool real = p0 < nt;
-                sOff[p0] = real ? (e0 >> 8) * gsStrideB : zoff;
+                sOff[p0] = real ? (e0 >> sh) * gsStrideB : off_first;
                 sCode[p0] = real ? ((s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0)) : 0;
+                sScale[p0] = real ? (cb ? 1.0f / (float)(((e0 >> sb) & cmask) + 1u) : 1.0f) : 0.f;
             }
             if (p1 < nt4) {
                 const bool real = p1 < nt;
-                sOff[p1] = real ? (e1 >> 8) * gsStrideB : zoff;
+                sOff[p1] = real ? (e1 >> sh) * gsStrideB : off_first;
                 sCode[p1] = real ? ((s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0)) : 0;
+                sScale[p1] = real ? (cb ? 1.0f / (float)(((e1 >> sb) & cmask) + 1u) : 1.0f) : 0.f;
             }
             __syncwarp();
             // software pipeline over batches of four gathers, 4*DEPTH strips in flight
@@ -506,7 +533,7 @@ static bool t_plan_main(int B, int N, int M, int F, int C, int r, const TGeom& g
     p.threads = nw * 32;
     if (nw % g.G) return false;
     p.per_cta = nw / g.G;
-    p.smem = ((size_t)F + (size_t)nw * g.SLOTS) * 32 * vec * sizeof(float) + (size_t)nw * 128 * sizeof(int);
+    p.smem = ((size_t)F + (size_t)nw * g.SLOTS) * 32 * vec * sizeof(float) + (size_t)nw * 192 * sizeof(int);
     if (p.smem > SMEM_CAP) return false;
     const long long rows = (long long)B * N;
     long long want = sm_count();
@@ -527,7 +554,7 @@ static inline unsigned grid_for(size_t work, int threads, int per_sm)
 }
 
 static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const int* nn_index, const int* nn_count,
-                        const int* bin_index, char* plan, cudaStream_t st, int* launches)
+                        const int* bin_index, char* plan, cudaStream_t st, int* launches, int code_k = 0)
 {
     int* seg = reinterpret_cast<int*>(plan + g.seg_off);
     int* sums = reinterpret_cast<int*>(plan + g.sums_off);
@@ -538,7 +565,7 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
     const unsigned ge = grid_for(slots, 256, 16);
     void* ranks = plan + g.rank_off;
 #define EDGES(FILL, RT)                                                                                                    \
-    transpose_edges_kernel<FILL, RT><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, nn_index,       \
+    transpose_edges_kernel<FILL, RT><<<ge, 256, 0, st>>>(slots, (unsigned)M, (unsigned)N, K, F, g.G, g.SLOTS, g.sb, g.cb, code_k, nn_index, \
                                                          nn_count, bin_index, seg, reinterpret_cast<RT*>(ranks), ent)
     if (g.rank_bytes == 2) EDGES(false, unsigned short); else EDGES(false, unsigned);
     SPH3D_CHECK_LAUNCH();
@@ -550,7 +577,7 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
 #undef EDGES
     SPH3D_CHECK_LAUNCH();
     *launches += 4;
-    if (tune_int("SPH3D_BWDT_SORT", 0) == 1) {             // opt-in: canonical order inside every segment
+    if (tunables().bwdt_sort == 1) {             // opt-in: canonical order inside every segment
         sort_segments_kernel<<<grid_for(g.nseg, 256, 16), 256, 0, st>>>(g.nseg, seg, ent);
         SPH3D_CHECK_LAUNCH();
         *launches += 1;
@@ -561,12 +588,12 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
 // workspace of the gradient call proper (scaled grad_output + filter partials), after an optional plan
 struct TWork { size_t gs_off, part_off, total; size_t P; };
 
-static TWork t_work(int B, int M, int F, int C, int r, const TPlanMain& p)
+static TWork t_work(int B, int M, int F, int C, int r, const TGeom& g, const TPlanMain& p)
 {
     TWork w{};
     const size_t Co = (size_t)C * r;
     w.gs_off = 0;
-    w.part_off = align256(((size_t)B * M + 1) * Co * sizeof(float));
+    w.part_off = g.fold ? 0 : align256(((size_t)B * M + 1) * Co * sizeof(float));   // no scaled copy when 1/cnt rides in the plan
     w.P = (size_t)p.grid_x * p.per_cta;
     w.total = w.part_off + align256(w.P * F * Co * sizeof(float));
     return w;
@@ -576,7 +603,7 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
                       const int* nn_count, const float* input, const float* filter, const float* grad_output,
                       float* grad_input, float* grad_filter, char* work, cudaStream_t st, int* launches)
 {
-    const TWork w = t_work(B, M, F, C, r, p);
+    const TWork w = t_work(B, M, F, C, r, g, p);
     const size_t Co = (size_t)C * r;
     float* gs = reinterpret_cast<float*>(work + w.gs_off);
     float* part = reinterpret_cast<float*>(work + w.part_off);
@@ -584,7 +611,9 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
     if (e != cudaSuccess) return (int)e;
-    {
+    const float* gsrc = grad_output;
+    if (!g.fold) {
+        gsrc = gs;
         const int V = (Co % 4 == 0) ? 4 : ((Co % 2 == 0) ? 2 : 1);
         const size_t orows = (size_t)B * M;
         const size_t total = (orows + 1) * Co / V;
@@ -596,12 +625,11 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     }
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * N);
-    const unsigned zrow = (unsigned)((long long)B * M);
 #define LAUNCH_T2(V, RR, TH, DP)                                                                                 \
     do {                                                                                                         \
         e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP>, p.smem);                                                  \
         if (e != cudaSuccess) return (int)e;                                                                     \
-        conv_bwd_t_kernel<V, RR, TH, DP><<<grid, TH, p.smem, st>>>(rows, zrow, F, C, g.G, g.SLOTS, seg, ent, gs, \
+        conv_bwd_t_kernel<V, RR, TH, DP><<<grid, TH, p.smem, st>>>(rows, g.sb, g.cb, F, C, g.G, g.SLOTS, seg, ent, gsrc, \
                                                                    input, filter, grad_input, part);             \
     } while (0)
     const int depth = t_depth(p.threads / 32);
@@ -625,7 +653,7 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     SPH3D_CHECK_LAUNCH();
     int rc = launch_reduce_partials((int)w.P, (size_t)F * Co, part, grad_filter, st);
     if (rc) return rc;
-    *launches += 3;
+    *launches += g.fold ? 2 : 3;
     return 0;
 }
 
@@ -635,7 +663,7 @@ bool bwd_transposed_supported(int B, int N, int M, int F, int C, int r, int K)
     // SPH3D_BWD_ALGO: unset = auto, 1 = row-owned form (conv_bwd.cu) everywhere, 2 = transposed form wherever it applies.
     // Auto: the transposed form gathers C*r floats per edge where the row-owned form gathers C and reduces C, so it
     // wins for r = 1 (measured) and is left to the planned entry points for r = 2.
-    const int algo = tune_int("SPH3D_BWD_ALGO", 0);
+    const int algo = tunables().bwd_algo;
     if (algo == 1) return false;
     if (algo != 2 && r != 1) return false;
     TPlanMain p;
@@ -647,7 +675,7 @@ size_t bwd_transposed_workspace_bytes(int B, int N, int M, int F, int C, int r, 
     const TGeom g = t_geom(B, N, M, F, K);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return 0;
-    return g.total + t_work(B, M, F, C, r, p).total;
+    return g.total + t_work(B, M, F, C, r, g, p).total;
 }
 
 int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const int* nn_index, const int* nn_count,
@@ -657,7 +685,7 @@ int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const in
     const TGeom g = t_geom(B, N, M, F, K);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return (int)cudaErrorInvalidValue;
-    if (!workspace || workspace_bytes < g.total + t_work(B, M, F, C, r, p).total) return (int)cudaErrorInvalidValue;
+    if (!workspace || workspace_bytes < g.total + t_work(B, M, F, C, r, g, p).total) return (int)cudaErrorInvalidValue;
     char* ws = reinterpret_cast<char*>(workspace);
     int launches = 0;
     int rc = t_build_plan(B, N, M, F, K, g, nn_index, nn_count, bin_index, ws, st, &launches);
@@ -666,6 +694,108 @@ int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const in
                     ws + g.total, st, &launches);
     g_last_launch_count = launches;
     return rc;
+}
+
+// ---------------------------------------------------------------- gather form of the pool / unpool gradients
+// avg-pool, mean- and weighted-interpolate backward are the same sum without bins:
+//      grad_input[b, s, :] = sum_{rows m, slots k : nn[b,m,k] = s} grad_output[b, m, :] * scale(m, k)
+// with scale = 1/nn_count[b,m] (avg / mean) or weight[b,m,k] (weighted).  The reference scatters with one float atomic
+// per edge and channel (tf_pool3d_gpu.cu:73-90, tf_unpool3d_gpu.cu:25-42, :66-84).  Here the graph is transposed with the
+// same three kernels as the convolution's (one bin, one class), then one warp per SOURCE point gathers the rows that
+// reference it: register sums, plain stores, no atomics, no zero fill.
+template <int VEC, bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+t_gather_kernel(unsigned rows /* B*S */, int sh, int sb, unsigned cmask, int C, int K, const int* __restrict__ seg,
+                const unsigned* __restrict__ entries, const float* __restrict__ weight,
+                const float* __restrict__ grad_output, float* __restrict__ grad_input)
+{
+    const int lane = threadIdx.x & 31;
+    const int c0 = blockIdx.y * 32 * VEC + lane * VEC;
+    const bool active = c0 < C;
+    const int c0ld = active ? c0 : 0;
+    const unsigned strideB = (unsigned)C * 4u;
+    const char* gb = reinterpret_cast<const char*>(grad_output) + (size_t)c0ld * 4;
+    const unsigned nw = gridDim.x * (blockDim.x >> 5);
+    for (unsigned row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nw) {
+        const int beg = __ldg(seg + row), end = __ldg(seg + row + 1);
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] = 0.f;
+        for (int kt = beg; kt < end; kt += 32) {
+            const int nk = min(32, end - kt);
+            unsigned myo = 0; float mys = 0.f;
+            if (lane < nk) {
+                const unsigned e = __ldg(entries + kt + lane);
+                const unsigned r = e >> sh, code = (e >> sb) & cmask;
+                myo = r * strideB;
+                mys = WEIGHTED ? __ldg(weight + (size_t)r * K + code) : 1.0f / (float)(code + 1u);
+            }
+            for (int kk = 0; kk < nk; kk += 8) {                    // eight row gathers in flight
+                unsigned o[8]; float sc[8]; float x[8][VEC];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int src = min(kk + u, nk - 1);
+                    o[u] = __shfl_sync(FULL_MASK, myo, src);
+                    sc[u] = (kk + u < nk) ? __shfl_sync(FULL_MASK, mys, src) : 0.f;   // tail slots re-read the last row with scale 0
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) ld_strip<VEC>(x[u], gb, o[u]);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[v] = fmaf(x[u][v], sc[u], acc[v]);
+            }
+        }
+        if (active) VecIO<VEC>::st(grad_input + (size_t)row * C + c0, acc);
+    }
+}
+
+// S = source points per cloud (rows of grad_input), R = referencing rows per cloud (rows of grad_output)
+static TGeom pool_geom(int B, int S, int R, int K)
+{
+    TGeom g = t_geom(B, S, R, 1, K);
+    if (g.ok && !g.fold) g.ok = false;                              // the scale code must ride in the entry
+    if (g.ok && ((long long)B * R * 4 >= (1LL << 30))) g.ok = false;
+    return g;
+}
+
+size_t pool_scatter_workspace_bytes(int B, int S, int R, int C, int K)
+{
+    if (B <= 0 || S <= 0 || R <= 0 || C <= 0 || K <= 0) return 0;
+    if ((long long)B * R * C * 4 >= (1LL << 32)) return 0;          // 32-bit byte offsets into grad_output
+    const TGeom g = pool_geom(B, S, R, K);
+    return g.ok ? g.total : 0;
+}
+
+int pool_scatter_run(int B, int S, int R, int C, int K, const int* nn_index, const int* nn_count, const float* weight,
+                     const float* grad_output, float* grad_input, void* workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    const TGeom g = pool_geom(B, S, R, K);
+    if (!g.ok || !workspace || workspace_bytes < g.total) return (int)cudaErrorInvalidValue;
+    char* plan = reinterpret_cast<char*>(workspace);
+    int launches = 0;
+    int rc = t_build_plan(B, S, R, 1, K, g, nn_index, nn_count, nullptr, plan, st, &launches, weight ? 1 : 0);
+    if (rc) return rc;
+    const int* seg = reinterpret_cast<const int*>(plan + g.seg_off);
+    const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
+    int vec = pick_vec_full_warp(C);
+    const int chunks = (C + 32 * vec - 1) / (32 * vec);
+    const unsigned rows = (unsigned)((long long)B * S);
+    long long want = (long long)sm_count() * 8 / chunks, tiles = ((long long)rows + 7) / 8;
+    if (want < 1) want = 1;
+    dim3 grid((unsigned)(tiles < want ? tiles : want), (unsigned)chunks);
+    const int sh = g.sb + g.cb;
+    const unsigned cmask = (1u << g.cb) - 1u;
+#define LAUNCH_TG(V)                                                                                                   \
+    do {                                                                                                               \
+        if (weight) t_gather_kernel<V, true><<<grid, 256, 0, st>>>(rows, sh, g.sb, cmask, C, K, seg, ent, weight, grad_output, grad_input); \
+        else t_gather_kernel<V, false><<<grid, 256, 0, st>>>(rows, sh, g.sb, cmask, C, K, seg, ent, weight, grad_output, grad_input);      \
+    } while (0)
+    if (vec == 4) LAUNCH_TG(4); else if (vec == 2) LAUNCH_TG(2); else LAUNCH_TG(1);
+#undef LAUNCH_TG
+    SPH3D_CHECK_LAUNCH();
+    g_last_launch_count = launches + 1;
+    return 0;
 }
 
 }  // namespace sph3d
@@ -696,7 +826,7 @@ extern "C" size_t sph3d_depthwise_conv3d_grad_planned_workspace_bytes(int B, int
     const TGeom g = t_geom(B, N, M, F, K);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return 0;
-    return t_work(B, M, F, C, r, p).total;
+    return t_work(B, M, F, C, r, g, p).total;
 }
 
 extern "C" int sph3d_depthwise_conv3d_grad_planned(int B, int N, int M, int F, int C, int r, int K, const int* nn_count,
@@ -709,7 +839,7 @@ extern "C" int sph3d_depthwise_conv3d_grad_planned(int B, int N, int M, int F, i
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return (int)cudaErrorInvalidValue;
     if (!nn_count || !plan || plan_bytes < g.total || !input || !filter || !grad_output || !grad_input || !grad_filter ||
-        !workspace || workspace_bytes < t_work(B, M, F, C, r, p).total)
+        !workspace || workspace_bytes < t_work(B, M, F, C, r, g, p).total)
         return (int)cudaErrorInvalidValue;
     int launches = 0;
     int rc = t_run_main(B, N, M, F, C, r, K, g, p, reinterpret_cast<const char*>(plan), nn_count, input, filter, grad_output,

@@ -168,16 +168,19 @@ static inline bool fits_32bit(int B, int N, int M, int C, int r)
 
 // rows are handed to CTAs in contiguous chunks so that the warps sharing an SM's L1 work on
 // neighbouring rows (the "first K by index" rule makes neighbouring rows share most neighbours)
-// Launch-shape tunables (defaults are what bench.py measures; the SPH3D_* environment variables exist
-// for the sweeps documented in DESIGN.md and are read once per call on the host).
-static inline int tune_int(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    int x = atoi(v);
-    return x > 0 ? x : dflt;
-}
-static inline int rows_per_chunk() { return tune_int("SPH3D_ROWS_PER_CHUNK", 128); }
+// Launch-shape tunables (defaults are what bench.py measures; the SPH3D_* environment variables exist for the sweeps
+// documented in DESIGN.md).  The environment is read ONCE, when the library is loaded, into this table; a process that
+// changes a variable afterwards (tests, sweep scripts) calls sph3d_reload_tunables().  0 = unset -> the default applies.
+struct Tunables {
+    int rows_per_chunk;                                  // SPH3D_ROWS_PER_CHUNK (pins the chunk size when set)
+    int fwd_threads, fwd_vec;                            // SPH3D_FWD_THREADS, SPH3D_FWD_VEC
+    int bwd_algo, bwd_vec, bwd_g, bwd_threads, bwd_cta_reduce;   // SPH3D_BWD_*  (row-owned backward)
+    int bwdt_threads, bwdt_depth, bwdt_g, bwdt_sort;     // SPH3D_BWDT_* (transposed backward)
+    int nnquery_grid;                                    // SPH3D_NNQUERY_GRID: -1 unset, 0 never, 2 whenever possible
+};
+const Tunables& tunables();                              // conv_fwd.cu
+static inline int tun(int v, int dflt) { return v > 0 ? v : dflt; }
+static inline int rows_per_chunk() { return tun(tunables().rows_per_chunk, 128); }
 
 // Chunk size for a problem of `rows` rows when `want` CTAs (per channel chunk) would fill the machine.  Large problems
 // keep the default (contiguous rows share neighbours, so long chunks keep the gathers in L1).  Small ones -- the deep
@@ -187,7 +190,7 @@ static inline int rows_per_chunk() { return tune_int("SPH3D_ROWS_PER_CHUNK", 128
 static inline int pick_rows_per_chunk(long long rows, long long want, int min_rows)
 {
     int rpc = rows_per_chunk();
-    if (getenv("SPH3D_ROWS_PER_CHUNK")) return rpc;                  // sweeps pin it
+    if (tunables().rows_per_chunk > 0) return rpc;                   // sweeps pin it
     const long long nchunks = (rows + rpc - 1) / rpc;
     if (nchunks >= want) return rpc;
     long long per = (rows + want - 1) / want;                        // rows per CTA if every SM gets one chunk
@@ -205,6 +208,12 @@ size_t bwd_transposed_workspace_bytes(int B, int N, int M, int F, int C, int r, 
 int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const int* nn_index, const int* nn_count,
                        const int* bin_index, const float* input, const float* filter, const float* grad_output,
                        float* grad_input, float* grad_filter, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// conv_bwd_t.cu: gather form of the avg-pool / mean- and weighted-interpolate gradients (pool3d.cu routes to it when the
+// caller provides scratch).  S = source points per cloud (grad_input rows), R = referencing rows per cloud.
+size_t pool_scatter_workspace_bytes(int B, int S, int R, int C, int K);
+int pool_scatter_run(int B, int S, int R, int C, int K, const int* nn_index, const int* nn_count, const float* weight,
+                     const float* grad_output, float* grad_input, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 template <typename Kern>
 static cudaError_t set_smem(Kern k, size_t bytes)

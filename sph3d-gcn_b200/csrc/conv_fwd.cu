@@ -27,7 +27,38 @@ namespace sph3d {
 
 thread_local int g_last_launch_count = 0;
 
-template <int VEC, int R>
+static int env_int(const char* name, int unset)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return unset;
+    return atoi(v);
+}
+static Tunables read_tunables()
+{
+    Tunables t{};
+    t.rows_per_chunk = env_int("SPH3D_ROWS_PER_CHUNK", 0);
+    t.fwd_threads = env_int("SPH3D_FWD_THREADS", 0);
+    t.fwd_vec = env_int("SPH3D_FWD_VEC", 0);
+    t.bwd_algo = env_int("SPH3D_BWD_ALGO", 0);
+    t.bwd_vec = env_int("SPH3D_BWD_VEC", 0);
+    t.bwd_g = env_int("SPH3D_BWD_G", 0);
+    t.bwd_threads = env_int("SPH3D_BWD_THREADS", 0);
+    t.bwd_cta_reduce = env_int("SPH3D_BWD_CTA_REDUCE", 0);
+    t.bwdt_threads = env_int("SPH3D_BWDT_THREADS", 0);
+    t.bwdt_depth = env_int("SPH3D_BWDT_DEPTH", 0);
+    t.bwdt_g = env_int("SPH3D_BWDT_G", 0);
+    t.bwdt_sort = env_int("SPH3D_BWDT_SORT", 0);
+    t.nnquery_grid = env_int("SPH3D_NNQUERY_GRID", -1);
+    return t;
+}
+static Tunables g_tunables = read_tunables();             // once, at library load
+const Tunables& tunables() { return g_tunables; }
+
+// PLANNED = false: nn_index / bin_index are the graph tensors and every 64-edge tile is counting-sorted by bin in
+// shared memory.  PLANNED = true: `nn_index` points at the sorted edge words written by conv_sort_kernel
+// (word = neighbour id << 8 | bin << 1 | last-of-its-bin), `bin_index` is unused, and the next row's words are
+// prefetched while the current row gathers.
+template <int VEC, int R, bool PLANNED>
 __global__ void __launch_bounds__(1024, 1)
 conv_fwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, int K,
                 const int* __restrict__ nn_index, const int* __restrict__ nn_count,
@@ -50,11 +81,11 @@ conv_fwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
     const size_t cloudB = (size_t)N * C * 4;
     const float* wlane = Wsh + S::offset(0, lane);
     const unsigned nchunks = (rows + rpc - 1) / rpc;
-    // per-warp scratch of the bin sort, behind the filter
+    // per-warp scratch behind the filter: the sorted tile (+ the histograms of the bin sort when it runs here)
     const int FP = ((F + 31) / 32) * 32;
-    int* hA = reinterpret_cast<int*>(Wsh + (size_t)F * S::FLOATS) + (size_t)warp * sort_smem_ints(F);
+    int* hA = reinterpret_cast<int*>(Wsh + (size_t)F * S::FLOATS) + (size_t)warp * (PLANNED ? 128 : sort_smem_ints(F));
     int* hB = hA + (FP + 1 + 3) / 4 * 4;
-    unsigned* sOff = reinterpret_cast<unsigned*>(hB + FP);
+    unsigned* sOff = PLANNED ? reinterpret_cast<unsigned*>(hA) : reinterpret_cast<unsigned*>(hB + FP);
     int* sCode = reinterpret_cast<int*>(sOff + 64);
 
     for (unsigned chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -64,8 +95,25 @@ conv_fwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
         if (row >= rend) continue;
         RowCursor cur;
         cur.init(row, M);
+        // planned form: count and first tile of the row after this one are loaded one row ahead
+        int cnt_n = 0;
+        unsigned w0_n = 0, w1_n = 0;
+        auto prefetch = [&](unsigned rw) {
+            cnt_n = min(__ldg(nn_count + rw), K);
+            const int* wr = nn_index + (size_t)rw * K;
+            w0_n = (lane < cnt_n) ? (unsigned)__ldg(wr + lane) : 0u;
+            w1_n = (32 + lane < cnt_n) ? (unsigned)__ldg(wr + 32 + lane) : 0u;
+        };
+        if constexpr (PLANNED) prefetch(row);
         for (; row < rend; row += nwarps, cur.advance(nwarps, M)) {
-            const int cnt = min(__ldg(nn_count + row), K);
+            int cnt;
+            unsigned w0_c = 0, w1_c = 0;
+            if constexpr (PLANNED) {
+                cnt = cnt_n; w0_c = w0_n; w1_c = w1_n;
+                if (row + nwarps < rend) prefetch(row + nwarps);
+            } else {
+                cnt = min(__ldg(nn_count + row), K);
+            }
             const char* inb = reinterpret_cast<const char*>(input) + cur.b * cloudB + (size_t)c0ld * 4;
             const int* idxrow = nn_index + (size_t)row * K;
             const int* binrow = bin_index + (size_t)row * K;
@@ -75,12 +123,23 @@ conv_fwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
 
             for (int kt = 0; kt < cnt; kt += 64) {
                 const int k0 = kt + lane, k1 = kt + 32 + lane;
-                unsigned o0 = 0, o1 = 0;
-                int b0 = -1, b1 = -1;
-                if (k0 < cnt) { o0 = (unsigned)__ldg(idxrow + k0) * strideB; b0 = __ldg(binrow + k0); }
-                if (k1 < cnt) { o1 = (unsigned)__ldg(idxrow + k1) * strideB; b1 = __ldg(binrow + k1); }
-                // group the tile's edges by bin (shared-memory counting sort), then one flat gather loop
-                sort_tile_by_bin(o0, b0, o1, b1, FP, lane, hA, hB, sOff, sCode);
+                if constexpr (PLANNED) {
+                    unsigned w0 = w0_c, w1 = w1_c;
+                    if (kt != 0) {                                // rows longer than one tile (K > 64): later tiles on demand
+                        w0 = (k0 < cnt) ? (unsigned)__ldg(idxrow + k0) : 0u;
+                        w1 = (k1 < cnt) ? (unsigned)__ldg(idxrow + k1) : 0u;
+                    }
+                    sOff[lane] = (w0 >> 8) * strideB;      sCode[lane] = (int)(w0 & 255u);
+                    sOff[32 + lane] = (w1 >> 8) * strideB; sCode[32 + lane] = (int)(w1 & 255u);
+                    __syncwarp();
+                } else {
+                    unsigned o0 = 0, o1 = 0;
+                    int b0 = -1, b1 = -1;
+                    if (k0 < cnt) { o0 = (unsigned)__ldg(idxrow + k0) * strideB; b0 = __ldg(binrow + k0); }
+                    if (k1 < cnt) { o1 = (unsigned)__ldg(idxrow + k1) * strideB; b1 = __ldg(binrow + k1); }
+                    // group the tile's edges by bin (shared-memory counting sort), then one flat gather loop
+                    sort_tile_by_bin(o0, b0, o1, b1, FP, lane, hA, hB, sOff, sCode);
+                }
                 const int nt = min(64, cnt - kt);
                 float s[VEC];
 #pragma unroll
@@ -139,6 +198,42 @@ conv_fwd_kernel(unsigned rows, unsigned rpc, int N, unsigned M, int F, int C, in
     }
 }
 
+// Graph-only half of the forward pass: every row's edges grouped by bin (ascending bin, original k order inside a bin;
+// tiles of 64 edges are sorted independently), packed as  neighbour id << 8 | bin << 1 | last-edge-of-its-bin  at the
+// edge's new position row*K + p.  Words beyond nn_count are not written.  One warp per row, same counting sort as the
+// one-call kernel, so the planned and the one-call forward sum in the same order (bit-identical outputs).
+__global__ void __launch_bounds__(256)
+conv_sort_kernel(unsigned rows, int K, int F, const int* __restrict__ nn_index, const int* __restrict__ nn_count,
+                 const int* __restrict__ bin_index, unsigned* __restrict__ words)
+{
+    extern __shared__ __align__(16) int ssm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int FP = ((F + 31) / 32) * 32;
+    int* hA = ssm + (size_t)warp * sort_smem_ints(F);
+    int* hB = hA + (FP + 1 + 3) / 4 * 4;
+    unsigned* sOff = reinterpret_cast<unsigned*>(hB + FP);
+    int* sCode = reinterpret_cast<int*>(sOff + 64);
+    for (unsigned row = blockIdx.x * nwarps + warp; row < rows; row += gridDim.x * nwarps) {
+        const int cnt = min(__ldg(nn_count + row), K);
+        const int* idxrow = nn_index + (size_t)row * K;
+        const int* binrow = bin_index + (size_t)row * K;
+        unsigned* wrow = words + (size_t)row * K;
+        for (int kt = 0; kt < cnt; kt += 64) {
+            const int k0 = kt + lane, k1 = kt + 32 + lane;
+            unsigned o0 = 0, o1 = 0;
+            int b0 = -1, b1 = -1;
+            if (k0 < cnt) { o0 = (unsigned)__ldg(idxrow + k0); b0 = __ldg(binrow + k0); }
+            if (k1 < cnt) { o1 = (unsigned)__ldg(idxrow + k1); b1 = __ldg(binrow + k1); }
+            if ((unsigned)b0 >= (unsigned)F) b0 = (k0 < cnt) ? 0 : -1;      // malformed bins fold into bin 0 (never out of bounds)
+            if ((unsigned)b1 >= (unsigned)F) b1 = (k1 < cnt) ? 0 : -1;
+            sort_tile_by_bin(o0, b0, o1, b1, FP, lane, hA, hB, sOff, sCode);
+            if (k0 < cnt) wrow[k0] = (sOff[lane] << 8) | (unsigned)sCode[lane];
+            if (k1 < cnt) wrow[k1] = (sOff[32 + lane] << 8) | (unsigned)sCode[32 + lane];
+            __syncwarp();
+        }
+    }
+}
+
 // generic fallback (any r, any F, any size): one thread per output element
 __global__ void __launch_bounds__(256)
 conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict__ nn_index,
@@ -160,16 +255,17 @@ conv_fwd_generic(int B, int N, int M, int C, int r, int K, const int* __restrict
     }
 }
 
-static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
+static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r, bool planned)
 {
     ConvPlan p{};
     if ((r != 1 && r != 2) || !fits_32bit(B, N, M, C, r) || F > 128) return p;
+    if (planned && N >= (1 << 24)) return p;                        // a sorted edge word keeps the neighbour id in 24 bits
     int vec = pick_vec_full_warp(C);
     {   // sweep knob: force a strip width (must divide C)
-        int v_env = tune_int("SPH3D_FWD_VEC", vec);
+        int v_env = tunables().fwd_vec > 0 ? tunables().fwd_vec : vec;
         if ((v_env == 1 || v_env == 2 || v_env == 4) && C % v_env == 0) vec = v_env;
     }
-    const size_t sort_bytes = (size_t)32 * sort_smem_ints(F) * sizeof(int);     // 32 warps
+    const size_t sort_bytes = (size_t)32 * (planned ? 128 : sort_smem_ints(F)) * sizeof(int);     // 32 warps
     size_t smem = (size_t)F * 32 * vec * r * sizeof(float);
     while (smem + sort_bytes > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
     if (smem + sort_bytes > SMEM_CAP) return p;
@@ -185,7 +281,7 @@ static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
     const long long nchunks = (rows + rpc - 1) / rpc;
     p.grid_x = (int)(nchunks < want ? nchunks : want);
     // small problems: fewer warps per CTA so that more SMs get work
-    p.threads = tune_int("SPH3D_FWD_THREADS", 1024);
+    p.threads = tun(tunables().fwd_threads, 1024);
     if (p.threads > 1024 || p.threads % 32) p.threads = 1024;
     while (p.threads > 128 && (long long)p.grid_x * p.chunks * (p.threads / 32) > rows && p.grid_x * p.chunks < sm_count())
         p.threads >>= 1;
@@ -196,17 +292,13 @@ static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r)
 
 using namespace sph3d;
 
-extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, int K,
-                                      const int* nn_index, const int* nn_count, const int* bin_index,
-                                      const float* input, const float* filter, float* output, void* stream)
+static int run_fwd(int B, int N, int M, int F, int C, int r, int K, const int* nn_index, const int* nn_count,
+                   const int* bin_index, const float* input, const float* filter, float* output, bool planned,
+                   cudaStream_t st)
 {
-    g_last_launch_count = 0;
-    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0 || !nn_index || !nn_count ||
-        !bin_index || !input || !filter || !output)
-        return (int)cudaErrorInvalidValue;
-    cudaStream_t st = (cudaStream_t)stream;
-    ConvPlan p = plan_fwd(B, N, M, F, C, r);
+    ConvPlan p = plan_fwd(B, N, M, F, C, r, planned);
     if (p.vec == 0) {
+        if (planned) return (int)cudaErrorInvalidValue;           // sph3d_conv_sort_bytes returned 0 for this shape
         size_t total = (size_t)B * M * C * r;
         size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
         conv_fwd_generic<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(B, N, M, C, r, K, nn_index, nn_count,
@@ -219,13 +311,17 @@ extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, 
     const unsigned rows = (unsigned)((long long)B * M);
     const unsigned rpc = (unsigned)p.rpc;
     cudaError_t e = cudaSuccess;
-#define LAUNCH_FWD(V, RR)                                                                           \
-    do {                                                                                             \
-        e = set_smem(conv_fwd_kernel<V, RR>, p.smem);                                                \
-        if (e != cudaSuccess) return (int)e;                                                         \
-        conv_fwd_kernel<V, RR><<<grid, p.threads, p.smem, st>>>(rows, rpc, N, (unsigned)M, F, C, K,  \
-                                                                nn_index, nn_count, bin_index,       \
-                                                                input, filter, output);              \
+#define LAUNCH_FWD2(V, RR, PL)                                                                          \
+    do {                                                                                                 \
+        e = set_smem(conv_fwd_kernel<V, RR, PL>, p.smem);                                                \
+        if (e != cudaSuccess) return (int)e;                                                             \
+        conv_fwd_kernel<V, RR, PL><<<grid, p.threads, p.smem, st>>>(rows, rpc, N, (unsigned)M, F, C, K,  \
+                                                                    nn_index, nn_count, bin_index,       \
+                                                                    input, filter, output);              \
+    } while (0)
+#define LAUNCH_FWD(V, RR)                                                                               \
+    do {                                                                                                 \
+        if (planned) LAUNCH_FWD2(V, RR, true); else LAUNCH_FWD2(V, RR, false);                           \
     } while (0)
     if (p.vec == 4 && r == 1) LAUNCH_FWD(4, 1);
     else if (p.vec == 4 && r == 2) LAUNCH_FWD(4, 2);
@@ -234,10 +330,67 @@ extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, 
     else if (p.vec == 1 && r == 1) LAUNCH_FWD(1, 1);
     else LAUNCH_FWD(1, 2);
 #undef LAUNCH_FWD
+#undef LAUNCH_FWD2
     SPH3D_CHECK_LAUNCH();
     g_last_launch_count = 1;
     return 0;
 }
 
+extern "C" int sph3d_depthwise_conv3d(int B, int N, int M, int F, int C, int r, int K,
+                                      const int* nn_index, const int* nn_count, const int* bin_index,
+                                      const float* input, const float* filter, float* output, void* stream)
+{
+    g_last_launch_count = 0;
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0 || !nn_index || !nn_count ||
+        !bin_index || !input || !filter || !output)
+        return (int)cudaErrorInvalidValue;
+    return run_fwd(B, N, M, F, C, r, K, nn_index, nn_count, bin_index, input, filter, output, false, (cudaStream_t)stream);
+}
+
+// ---- split form of the forward launcher: graph-only sort + planned convolution -------------------------------------
+extern "C" size_t sph3d_conv_sort_bytes(int B, int N, int M, int F, int K)
+{
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || K <= 0 || F > 128 || N >= (1 << 24)) return 0;
+    if ((long long)B * M >= (1LL << 31)) return 0;
+    return (size_t)B * M * K * sizeof(unsigned);
+}
+
+extern "C" int sph3d_conv_sort(int B, int N, int M, int F, int K, const int* nn_index, const int* nn_count,
+                               const int* bin_index, void* plan, size_t plan_bytes, void* stream)
+{
+    g_last_launch_count = 0;
+    const size_t need = sph3d_conv_sort_bytes(B, N, M, F, K);
+    if (!need || !nn_index || !nn_count || !bin_index || !plan || plan_bytes < need) return (int)cudaErrorInvalidValue;
+    const unsigned rows = (unsigned)((long long)B * M);
+    const int warps = 8;
+    const size_t smem = (size_t)warps * sort_smem_ints(F) * sizeof(int);
+    unsigned want = (rows + warps - 1) / warps, cap = (unsigned)sm_count() * 8;
+    conv_sort_kernel<<<want < cap ? want : cap, warps * 32, smem, (cudaStream_t)stream>>>(
+        rows, K, F, nn_index, nn_count, bin_index, reinterpret_cast<unsigned*>(plan));
+    SPH3D_CHECK_LAUNCH();
+    g_last_launch_count = 1;
+    return 0;
+}
+
+extern "C" int sph3d_depthwise_conv3d_planned(int B, int N, int M, int F, int C, int r, int K, const int* nn_count,
+                                              const void* plan, size_t plan_bytes, const float* input,
+                                              const float* filter, float* output, void* stream)
+{
+    g_last_launch_count = 0;
+    if (B <= 0 || N <= 0 || M <= 0 || F <= 0 || C <= 0 || r <= 0 || K <= 0 || !nn_count || !plan || !input || !filter || !output)
+        return (int)cudaErrorInvalidValue;
+    const size_t need = sph3d_conv_sort_bytes(B, N, M, F, K);
+    if (!need || plan_bytes < need) return (int)cudaErrorInvalidValue;
+    return run_fwd(B, N, M, F, C, r, K, reinterpret_cast<const int*>(plan), nn_count, nullptr, input, filter, output, true,
+                   (cudaStream_t)stream);
+}
+
+extern "C" size_t sph3d_depthwise_conv3d_planned_supported(int B, int N, int M, int F, int C, int r, int K)
+{
+    if (!sph3d_conv_sort_bytes(B, N, M, F, K) || C <= 0) return 0;
+    return plan_fwd(B, N, M, F, C, r, true).vec != 0 ? 1 : 0;
+}
+
 extern "C" int sph3d_abi_version(void) { return SPH3D_B200_ABI_VERSION; }
+extern "C" void sph3d_reload_tunables(void) { g_tunables = read_tunables(); }
 extern "C" int sph3d_last_launch_count(void) { return g_last_launch_count; }

@@ -19,7 +19,7 @@
 //    Phase 2 (one warp per chain, exits at once when the chain has no empty query) replays only
 //    the chains in which some query found nothing, with the exact carried radius.
 #include <cstdlib>
-#include "common.cuh"
+#include "conv_common.cuh"
 #include "../../include/sph3d_b200.h"
 
 namespace sph3d {
@@ -507,9 +507,9 @@ using namespace sph3d;
 // workspace layout: GridInfo[B] | cell_start[B][GRID_CELLS+1] | cell_cursor[B][GRID_CELLS+1] | cell_pts[B][N]
 static bool grid_applicable(int N)
 {
-    const char* v = getenv("SPH3D_NNQUERY_GRID");          // 0 = never, 2 = whenever possible (tests), else auto
-    if (v && v[0] == '0') return false;
-    const int min_n = (v && v[0] == '2') ? 32 : GRID_MIN_N;
+    const int v = tunables().nnquery_grid;                 // SPH3D_NNQUERY_GRID: 0 = never, 2 = whenever possible (tests), else auto
+    if (v == 0) return false;
+    const int min_n = (v == 2) ? 32 : GRID_MIN_N;
     // per-warp bitmap of N bits, 8 warps per CTA, within the shared-memory budget
     return N >= min_n && (size_t)((N + 31) / 32) * 4 * 8 <= 200 * 1024;
 }

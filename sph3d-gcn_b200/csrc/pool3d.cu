@@ -15,7 +15,7 @@
 //
 // max-pool keeps the reference's selection rule exactly (Q11): neighbour 0 initialises, a later
 // neighbour replaces only if strictly greater, max_index is the database point id.
-#include "rowwarp.cuh"
+#include "conv_common.cuh"
 #include "../../include/sph3d_b200.h"
 
 namespace sph3d {
@@ -159,16 +159,6 @@ max_pool_grad_kernel(int B, int N, int M, int C, const int* __restrict__ max_ind
     }
 }
 
-// narrowest legal strip whose single chunk covers C, so that small channel counts still use all 32 lanes
-// (same rule as the convolution, conv_common.cuh::pick_vec_full_warp)
-static inline int pick_vec(int C)
-{
-    const int widest = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
-    for (int v = 1; v <= widest; v <<= 1)
-        if (C % v == 0 && C <= 32 * v) return v;
-    return widest;
-}
-
 static dim3 row_grid(int B, int rows_per_cloud, int C, int vec)
 {
     int chunks = (C + 32 * vec - 1) / (32 * vec);
@@ -182,7 +172,7 @@ template <int OP>
 static int launch_gather(int B, int S, int Rr, int C, int K, const int* nn_index, const int* nn_count,
                          const float* weight, const float* input, float* output, int* max_index, cudaStream_t st)
 {
-    int vec = pick_vec(C);
+    int vec = pick_vec_full_warp(C);
     dim3 grid = row_grid(B, Rr, C, vec);
     if (vec == 4) row_gather_kernel<4, OP><<<grid, POOL_WARPS * 32, 0, st>>>(B, S, Rr, C, K, nn_index, nn_count, weight, input, output, max_index);
     else if (vec == 2) row_gather_kernel<2, OP><<<grid, POOL_WARPS * 32, 0, st>>>(B, S, Rr, C, K, nn_index, nn_count, weight, input, output, max_index);
@@ -198,7 +188,7 @@ static int launch_scatter(int B, int S, int Rr, int C, int K, const int* nn_inde
 {
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * S * C, st);
     if (e != cudaSuccess) return (int)e;
-    int vec = pick_vec(C);
+    int vec = pick_vec_full_warp(C);
     dim3 grid = row_grid(B, Rr, C, vec);
     if (vec == 4) row_scatter_kernel<4, OP><<<grid, POOL_WARPS * 32, 0, st>>>(B, S, Rr, C, K, nn_index, nn_count, weight, grad_output, grad_input);
     else if (vec == 2) row_scatter_kernel<2, OP><<<grid, POOL_WARPS * 32, 0, st>>>(B, S, Rr, C, K, nn_index, nn_count, weight, grad_output, grad_input);
@@ -245,11 +235,24 @@ extern "C" int sph3d_avg_pool3d(int B, int N, int M, int C, int K, const int* nn
     return launch_gather<OP_MEAN>(B, N, M, C, K, nn_index, nn_count, nullptr, input, output, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" size_t sph3d_avg_pool3d_grad_workspace_bytes(int B, int N, int M, int C, int K)
+{
+    return pool_scatter_workspace_bytes(B, N, M, C, K);
+}
+extern "C" size_t sph3d_interpolate_grad_workspace_bytes(int B, int N, int M, int C, int K)
+{
+    return pool_scatter_workspace_bytes(B, M, N, C, K);
+}
+
 extern "C" int sph3d_avg_pool3d_grad(int B, int N, int M, int C, int K, const int* nn_index, const int* nn_count,
-                                     const float* grad_output, float* grad_input, void* stream)
+                                     const float* grad_output, float* grad_input,
+                                     void* workspace, size_t workspace_bytes, void* stream)
 {
     g_last_launch_count = 0;
     if (BAD5(B, N, M, C, K) || !nn_index || !nn_count || !grad_output || !grad_input) return (int)cudaErrorInvalidValue;
+    if (workspace && workspace_bytes && pool_scatter_workspace_bytes(B, N, M, C, K))
+        return pool_scatter_run(B, N, M, C, K, nn_index, nn_count, nullptr, grad_output, grad_input, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
     return launch_scatter<OP_MEAN>(B, N, M, C, K, nn_index, nn_count, nullptr, grad_output, grad_input, (cudaStream_t)stream);
 }
 
@@ -263,10 +266,14 @@ extern "C" int sph3d_mean_interpolate(int B, int N, int M, int C, int K, const i
 }
 
 extern "C" int sph3d_mean_interpolate_grad(int B, int N, int M, int C, int K, const int* nn_index,
-                                           const int* nn_count, const float* grad_output, float* grad_input, void* stream)
+                                           const int* nn_count, const float* grad_output, float* grad_input,
+                                           void* workspace, size_t workspace_bytes, void* stream)
 {
     g_last_launch_count = 0;
     if (BAD5(B, N, M, C, K) || !nn_index || !nn_count || !grad_output || !grad_input) return (int)cudaErrorInvalidValue;
+    if (workspace && workspace_bytes && pool_scatter_workspace_bytes(B, M, N, C, K))
+        return pool_scatter_run(B, M, N, C, K, nn_index, nn_count, nullptr, grad_output, grad_input, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
     return launch_scatter<OP_MEAN>(B, M, N, C, K, nn_index, nn_count, nullptr, grad_output, grad_input, (cudaStream_t)stream);
 }
 
@@ -281,9 +288,12 @@ extern "C" int sph3d_weighted_interpolate(int B, int N, int M, int C, int K, con
 
 extern "C" int sph3d_weighted_interpolate_grad(int B, int N, int M, int C, int K, const int* nn_index,
                                                const int* nn_count, const float* grad_output, const float* weight,
-                                               float* grad_input, void* stream)
+                                               float* grad_input, void* workspace, size_t workspace_bytes, void* stream)
 {
     g_last_launch_count = 0;
     if (BAD5(B, N, M, C, K) || !nn_index || !nn_count || !grad_output || !weight || !grad_input) return (int)cudaErrorInvalidValue;
+    if (workspace && workspace_bytes && pool_scatter_workspace_bytes(B, M, N, C, K))
+        return pool_scatter_run(B, M, N, C, K, nn_index, nn_count, weight, grad_output, grad_input, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
     return launch_scatter<OP_WEIGHTED>(B, M, N, C, K, nn_index, nn_count, weight, grad_output, grad_input, (cudaStream_t)stream);
 }

@@ -5,6 +5,12 @@ from .. import _lib
 from .tf_nnquery import _xyz
 
 
+# Graph-build side of the convolution plans (tf_conv3d.emit_plans): with this switch on, spherical_kernel also writes
+# the per-row bin-sorted edge words (forward) and, when EMIT_PLANS == "train", the transposed graph (backward) of the
+# graph it has just binned, so that the convolutions over that graph start from them.
+EMIT_PLANS = False
+
+
 @torch.no_grad()
 def spherical_kernel(database, query, nn_index, nn_count, nn_dist, radius, kernel=[8, 2, 3]):
     """Spherical-kernel bin of every edge of a ball-query graph.
@@ -38,4 +44,7 @@ def spherical_kernel(database, query, nn_index, nn_count, nn_dist, radius, kerne
                                                _lib.ptr(query), _lib.ptr(nn_index), _lib.ptr(nn_count),
                                                _lib.ptr(nn_dist), _lib.ptr(filt_index), _lib.stream_ptr())
     _lib.check(rc, "spherical_kernel")
+    if EMIT_PLANS:
+        from . import tf_conv3d
+        tf_conv3d.emit_plans(nn_index, nn_count, filt_index, n * p * q + 1, N, backward=(EMIT_PLANS == "train"))
     return filt_index

@@ -18,10 +18,14 @@ def _check(input, filter, nn_index, nn_count, bin_index):
     return input, filter, nn_index, nn_count, bin_index
 
 
-def _forward(input, filter, nn_index, nn_count, bin_index):
+def _forward(input, filter, nn_index, nn_count, bin_index, graph=None):
     B, N, C = input.shape
     F, _, r = filter.shape
     M, K = nn_index.shape[1], nn_index.shape[2]
+    if SHARE_PLANS and graph is not None and _lib.lib().sph3d_depthwise_conv3d_planned_supported(B, N, M, F, C, r, K):
+        plan = _shared_plan("fwd", graph[0], graph[1], graph[2], F, N)
+        if plan is not None:
+            return depthwise_conv3d_planned(input, filter, nn_count, plan, K)
     output = torch.empty((B, M, C * r), dtype=torch.float32, device=input.device)
     with torch.cuda.device(input.device):
         rc = _lib.lib().sph3d_depthwise_conv3d(B, N, M, F, C, r, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
@@ -52,6 +56,50 @@ def depthwise_conv3d_grad(input, filter, grad_output, nn_index, nn_count, bin_in
                                            _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
     _lib.check(rc, "depthwise_conv3d_grad")
     return grad_input, grad_filter
+
+
+def conv_sort(nn_index, nn_count, bin_index, num_bins, npoint):
+    """Graph-only half of the forward pass (sph3d_conv_sort): every row's edges grouped by bin, packed as one int32
+    word per edge.  Returns an opaque plan tensor for depthwise_conv3d_planned, or None where the planned form does
+    not apply (num_bins > 128).  Depends only on the graph and num_bins."""
+    nn_index = _lib.cuda_tensor(nn_index, torch.int32, 3, "nn_index")
+    nn_count = _lib.cuda_tensor(nn_count, torch.int32, 2, "nn_count")
+    bin_index = _lib.cuda_tensor(bin_index, torch.int32, 3, "bin_index")
+    if bin_index.shape != nn_index.shape or nn_count.shape != nn_index.shape[:2]:
+        raise ValueError("nn_index / nn_count / bin_index shapes are inconsistent")
+    B, M, K = nn_index.shape
+    npoint, num_bins = int(npoint), int(num_bins)
+    L = _lib.lib()
+    nbytes = L.sph3d_conv_sort_bytes(B, npoint, M, num_bins, K)
+    if nbytes == 0:
+        return None
+    plan = torch.empty((nbytes // 4,), dtype=torch.int32, device=nn_index.device)
+    with torch.cuda.device(nn_index.device):
+        rc = L.sph3d_conv_sort(B, npoint, M, num_bins, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
+                               _lib.ptr(bin_index), _lib.ptr(plan), nbytes, _lib.stream_ptr())
+    _lib.check(rc, "conv_sort")
+    return plan
+
+
+def depthwise_conv3d_planned(input, filter, nn_count, plan, nnsample):
+    """depthwise_conv3d with the per-row bin grouping hoisted out (plan from conv_sort); same values bit for bit."""
+    input = _lib.cuda_tensor(input, torch.float32, 3, "input")
+    filter = _lib.cuda_tensor(filter, torch.float32, 3, "filter")
+    nn_count = _lib.cuda_tensor(nn_count, torch.int32, 2, "nn_count")
+    B, N, C = input.shape
+    F, _, r = filter.shape
+    M, K = nn_count.shape[1], int(nnsample)
+    if filter.shape[1] != C:
+        raise ValueError("Input Channel size error of the filter")
+    L = _lib.lib()
+    if plan is None or not L.sph3d_depthwise_conv3d_planned_supported(B, N, M, F, C, r, K):
+        raise ValueError("the planned convolution does not cover this shape; use depthwise_conv3d")
+    output = torch.empty((B, M, C * r), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        rc = L.sph3d_depthwise_conv3d_planned(B, N, M, F, C, r, K, _lib.ptr(nn_count), _lib.ptr(plan), plan.numel() * 4,
+                                              _lib.ptr(input), _lib.ptr(filter), _lib.ptr(output), _lib.stream_ptr())
+    _lib.check(rc, "depthwise_conv3d_planned")
+    return output
 
 
 def conv_transpose(nn_index, nn_count, bin_index, num_bins, npoint):
@@ -109,26 +157,37 @@ def depthwise_conv3d_grad_planned(input, filter, grad_output, nn_count, plan, nn
 
 
 # Plan sharing.  The reference's models apply two convolutions per level over one graph (models/SPH3D_*.py call
-# separable_conv3d twice with the same nn_index / nn_count / filt_index), so their two gradients can share one
-# transposed graph.  With SHARE_PLANS on, the plan is built at the first backward pass that needs it and kept as an
-# attribute of the bin_index tensor OBJECT (it lives and dies with the graph; in-place edits of an index tensor change
-# its _version and invalidate it).  bench.py switches this off: its steps reuse one graph, and a plan surviving
-# from step to step would be work skipped inside the timed region.
+# separable_conv3d twice with the same nn_index / nn_count / filt_index), so their forward passes can share one sorted
+# edge list and their gradients one transposed graph.  With SHARE_PLANS on, a plan is built at the first pass that needs
+# it -- or by tf_buildkernel.spherical_kernel itself when its EMIT_PLANS switch is on (the graph-build side) -- and kept
+# as an attribute of the bin_index tensor OBJECT (it lives and dies with the graph; in-place edits of an index tensor
+# change its _version and invalidate it).  With SHARE_PLANS off every call runs the one-call entry points.
 SHARE_PLANS = True
+_BUILDERS = {"fwd": lambda *a: conv_sort(*a), "bwd": lambda *a: conv_transpose(*a)}
 
 
-def _shared_plan(nn_index, nn_count, bin_index, num_bins, npoint):
-    key = (int(num_bins), int(npoint), tuple(nn_index.shape), nn_index.data_ptr(), nn_count.data_ptr(),
+def _shared_plan(kind, nn_index, nn_count, bin_index, num_bins, npoint):
+    key = (kind, int(num_bins), int(npoint), tuple(nn_index.shape), nn_index.data_ptr(), nn_count.data_ptr(),
            nn_index._version, nn_count._version, bin_index._version)
     cache = getattr(bin_index, "_sph3d_plans", None)
     if cache is not None and key in cache:
         return cache[key]
-    plan = conv_transpose(nn_index, nn_count, bin_index, num_bins, npoint)
+    plan = _BUILDERS[kind](nn_index, nn_count, bin_index, num_bins, npoint)
     try:
-        bin_index._sph3d_plans = {key: plan}          # one plan per graph: a changed key replaces the stale one
+        if cache is None or any(k[1:] != key[1:] for k in cache):       # a changed graph replaces the stale plans
+            cache = {}
+            bin_index._sph3d_plans = cache
+        cache[key] = plan
     except Exception:                                    # objects that refuse attributes: no sharing, still correct
         pass
     return plan
+
+
+def emit_plans(nn_index, nn_count, bin_index, num_bins, npoint, backward=True):
+    """build the graph-only plans of the convolution now (graph-build side) and hang them off bin_index"""
+    _shared_plan("fwd", nn_index, nn_count, bin_index, num_bins, npoint)
+    if backward:
+        _shared_plan("bwd", nn_index, nn_count, bin_index, num_bins, npoint)
 
 
 def _use_planned(C, r):
@@ -142,7 +201,7 @@ class _DepthwiseConv3d(torch.autograd.Function):
     def forward(ctx, input, filter, nn_index, nn_count, bin_index):
         ctx.save_for_backward(input, filter, nn_index, nn_count, bin_index)
         ctx.graph = (nn_index, nn_count, bin_index)      # the tensor OBJECTS (a shared plan hangs off bin_index)
-        return _forward(input, filter, nn_index, nn_count, bin_index)
+        return _forward(input, filter, nn_index, nn_count, bin_index, ctx.graph)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -155,7 +214,7 @@ class _DepthwiseConv3d(torch.autograd.Function):
             B, N = input.shape[0], input.shape[1]
             M, K = g_idx.shape[1], g_idx.shape[2]
             if L.sph3d_depthwise_conv3d_grad_planned_workspace_bytes(B, N, M, F, C, r, K) > 0:
-                plan = _shared_plan(g_idx, g_cnt, g_bin, F, N)
+                plan = _shared_plan("bwd", g_idx, g_cnt, g_bin, F, N)
                 if plan is not None:
                     gi, gf = depthwise_conv3d_grad_planned(input, filter, grad_output, g_cnt, plan, K)
                     return gi, gf, None, None, None
@@ -164,15 +223,13 @@ class _DepthwiseConv3d(torch.autograd.Function):
 
 
 def depthwise_conv3d(input, filter, nn_index, nn_count, bin_index):
-    '''
-    Input:
-        input:   (batch, npoint, in_channels) float32 array, input point features
-        filter: (binsize, in_channels, channel_multiplier) float32 array, convolution filter
-        nn_index: (batch, mpoint, nnsample) int32 array, neighbor indices
-        nn_count: (batch, mpoint) int32 array, number of neighbors
-        bin_index: (batch, mpoint, nnsample), filtet bins' indices
-    Output:
-        output: (batch, mpoint, out_channels) float32 array, output point features
-    '''
+    """Depthwise spherical convolution over a neighbour graph (differentiable in `input` and `filter`).
+
+    input (B, N, C) float32 features of the database cloud; filter (F, C, r) float32, one C x r slab per spherical bin;
+    nn_index (B, M, K) int32 neighbour ids of each of the M query points, nn_count (B, M) int32 how many of the K slots
+    are valid, bin_index (B, M, K) int32 the bin of every edge (output of spherical_kernel).
+    Returns (B, M, C*r) float32: channel c*r+j of a query point is the mean over its valid edges of
+    input[neighbour, c] * filter[bin, c, j].
+    """
     input, filter, nn_index, nn_count, bin_index = _check(input, filter, nn_index, nn_count, bin_index)
     return _DepthwiseConv3d.apply(input, filter, nn_index, nn_count, bin_index)

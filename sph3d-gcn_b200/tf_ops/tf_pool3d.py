@@ -27,15 +27,23 @@ def max_pool3d_grad(input, grad_output, max_index):
     return grad_input
 
 
+# True: the gradient transposes the graph and gathers (no atomics); False: vector-reduction scatter (csrc/pool3d.cu)
+GATHER_FORM_GRAD = True
+
+
 def avg_pool3d_grad(input, grad_output, nn_index, nn_count):
     input, nn_index, nn_count = _check(input, nn_index, nn_count)
     grad_output = _lib.cuda_tensor(grad_output, torch.float32, 3, "grad_output")
     B, N, C = input.shape
     M, K = nn_index.shape[1], nn_index.shape[2]
     grad_input = torch.empty((B, N, C), dtype=torch.float32, device=input.device)
+    L = _lib.lib()
+    ws_bytes = L.sph3d_avg_pool3d_grad_workspace_bytes(B, N, M, C, K) if GATHER_FORM_GRAD else 0
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.int32, device=input.device) if ws_bytes else None
     with torch.cuda.device(input.device):
-        rc = _lib.lib().sph3d_avg_pool3d_grad(B, N, M, C, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
-                                              _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.stream_ptr())
+        rc = L.sph3d_avg_pool3d_grad(B, N, M, C, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
+                                     _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.ptr(ws), ws_bytes,
+                                     _lib.stream_ptr())
     _lib.check(rc, "avg_pool3d_grad")
     return grad_input
 

@@ -23,14 +23,25 @@ def _dims(input, nn_index):
     return B, nn_index.shape[1], M, C, nn_index.shape[2]
 
 
+# True: the gradients transpose the graph and gather (no atomics); False: vector-reduction scatter (csrc/pool3d.cu)
+GATHER_FORM_GRAD = True
+
+
+def _scratch(B, N, M, C, K, device):
+    nbytes = _lib.lib().sph3d_interpolate_grad_workspace_bytes(B, N, M, C, K) if GATHER_FORM_GRAD else 0
+    return (torch.empty((nbytes // 4,), dtype=torch.int32, device=device) if nbytes else None), nbytes
+
+
 def mean_interpolate_grad(input, grad_output, nn_index, nn_count):
     input, nn_index, nn_count, _ = _check(input, nn_index, nn_count)
     grad_output = _lib.cuda_tensor(grad_output, torch.float32, 3, "grad_output")
     B, N, M, C, K = _dims(input, nn_index)
     grad_input = torch.empty((B, M, C), dtype=torch.float32, device=input.device)
+    ws, ws_bytes = _scratch(B, N, M, C, K, input.device)
     with torch.cuda.device(input.device):
         rc = _lib.lib().sph3d_mean_interpolate_grad(B, N, M, C, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
-                                                    _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.stream_ptr())
+                                                    _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.ptr(ws), ws_bytes,
+                                                    _lib.stream_ptr())
     _lib.check(rc, "mean_interpolate_grad")
     return grad_input
 
@@ -40,10 +51,11 @@ def weighted_interpolate_grad(input, grad_output, weight, nn_index, nn_count):
     grad_output = _lib.cuda_tensor(grad_output, torch.float32, 3, "grad_output")
     B, N, M, C, K = _dims(input, nn_index)
     grad_input = torch.empty((B, M, C), dtype=torch.float32, device=input.device)
+    ws, ws_bytes = _scratch(B, N, M, C, K, input.device)
     with torch.cuda.device(input.device):
         rc = _lib.lib().sph3d_weighted_interpolate_grad(B, N, M, C, K, _lib.ptr(nn_index), _lib.ptr(nn_count),
                                                         _lib.ptr(grad_output), _lib.ptr(weight),
-                                                        _lib.ptr(grad_input), _lib.stream_ptr())
+                                                        _lib.ptr(grad_input), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
     _lib.check(rc, "weighted_interpolate_grad")
     return grad_input
 

@@ -17,14 +17,16 @@ A = lambda t: t.detach().cpu().numpy()
 
 
 @pytest.fixture()
-def force_grid():
+def force_grid(pkg):
     old = os.environ.get("SPH3D_NNQUERY_GRID")
     os.environ["SPH3D_NNQUERY_GRID"] = "2"
+    pkg._lib.reload_tunables()            # the library reads its tunables once, at load
     yield
     if old is None:
         os.environ.pop("SPH3D_NNQUERY_GRID", None)
     else:
         os.environ["SPH3D_NNQUERY_GRID"] = old
+    pkg._lib.reload_tunables()
 
 
 @pytest.mark.parametrize("case", SPHERE_CASES, ids=[c[0] for c in SPHERE_CASES])

@@ -232,7 +232,11 @@ def _plan_layout(B, N, M, F, K):
     a256 = lambda x: (x + 255) // 256 * 256
     sums_off = a256(nseg_pad * 4)
     ent_off = sums_off + a256(nseg_pad // 4096 * 4)
-    return G, SL, FP, nseg, ent_off // 4
+    sb = max(1, (SL - 1).bit_length())
+    cb = max(1, (K - 1).bit_length())
+    if B * M > (1 << (32 - sb - cb)):
+        cb = 0
+    return G, SL, FP, nseg, ent_off // 4, sb, cb
 
 
 TRANSPOSE_CASES = [c for c in CONV_CASES if c[0] in ("c128_r1", "c64_r2", "k156_tiles", "c6_r1_vec2")] + [
@@ -241,10 +245,10 @@ TRANSPOSE_CASES = [c for c in CONV_CASES if c[0] in ("c128_r1", "c64_r2", "k156_
 
 @pytest.mark.parametrize("canonical", [0, 1])
 @pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
-def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
+def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch, tune):
     """the transposed graph holds every edge exactly once, grouped by (input point, bin class, bin); with
     SPH3D_BWDT_SORT=1 additionally in ascending m inside a segment"""
-    monkeypatch.setenv("SPH3D_BWDT_SORT", str(canonical))
+    tune(SPH3D_BWDT_SORT=str(canonical))
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     B, N, _ = x.shape
     M, K, F = idx.shape[1], idx.shape[2], W.shape[0]
@@ -252,13 +256,15 @@ def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
     plan = pkg.tf_conv3d.conv_transpose(T(idx), T(cnt), T(filt), F, N)
     assert plan is not None
     plan = A(plan)
-    G, SL, FP, nseg, ent_w = _plan_layout(B, N, M, F, K)
+    G, SL, FP, nseg, ent_w, sb, cb = _plan_layout(B, N, M, F, K)
     seg_start = plan[:nseg + 1].astype(np.int64)
     b, m, k = np.nonzero(np.arange(K)[None, None, :] < np.minimum(cnt, K)[:, :, None])
     n, f = idx[b, m, k].astype(np.int64), filt[b, m, k].astype(np.int64)
     key = (b * N + n) * FP + (f % G) * SL + f // G
     order = np.lexsort((m, key))
-    want_entries = (((b[order] * M + m[order]).astype(np.int64) << 8) | (f[order] // G)).astype(np.uint32)
+    # entry = output row << (sb+cb) | (nn_count-1) << sb | bin slot: the 1/cnt scale rides in the plan when the bits allow
+    cm1 = (np.minimum(cnt, K)[b[order], m[order]].astype(np.int64) - 1) << sb if cb else 0
+    want_entries = (((b[order] * M + m[order]).astype(np.int64) << (sb + cb)) | cm1 | (f[order] // G)).astype(np.uint32)
     counts = np.bincount(key, minlength=nseg)
     assert_equal(seg_start, np.concatenate([[0], np.cumsum(counts)]), case[0] + " segment starts + total")
     got = plan[ent_w:ent_w + len(want_entries)].view(np.uint32)
@@ -269,10 +275,10 @@ def test_conv_transpose_plan(case, canonical, pkg, oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("case", TRANSPOSE_CASES, ids=[c[0] for c in TRANSPOSE_CASES])
-def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch):
+def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch, tune):
     """the split form (plan built once, reused) equals the one-call form; with canonical segment order
     (SPH3D_BWDT_SORT=1; the point-to-warp assignment is static) bit for bit in grad_filter"""
-    monkeypatch.setenv("SPH3D_BWDT_SORT", "1")
+    tune(SPH3D_BWDT_SORT="1")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
     ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
@@ -281,16 +287,16 @@ def test_depthwise_conv3d_backward_planned(case, pkg, oracle, monkeypatch):
         gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad_planned(T(x), T(W), T(go), T(cnt), plan, idx.shape[2])
         assert_close(A(gi), ti, 1e-5, case[0] + " planned grad_input")
         assert_close(A(gf), tf, 1e-5, case[0] + " planned grad_filter")
-    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
+    tune(SPH3D_BWD_ALGO="2")
     gi1, gf1 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
     assert_equal(A(gf), A(gf1), case[0] + " planned vs one-call grad_filter")
 
 
 @pytest.mark.parametrize("case", TRANSPOSE_CASES[:4], ids=[c[0] for c in TRANSPOSE_CASES[:4]])
-def test_transposed_backward_32_warp_configuration(case, pkg, oracle, monkeypatch):
+def test_transposed_backward_32_warp_configuration(case, pkg, oracle, monkeypatch, tune):
     """SPH3D_BWDT_THREADS=1024: 32 warps per CTA, 4 gathers in flight, bin classes dividing 32"""
-    monkeypatch.setenv("SPH3D_BWDT_THREADS", "1024")
-    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
+    tune(SPH3D_BWDT_THREADS="1024")
+    tune(SPH3D_BWD_ALGO="2")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
     ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
@@ -299,10 +305,10 @@ def test_transposed_backward_32_warp_configuration(case, pkg, oracle, monkeypatc
 
 
 @pytest.mark.parametrize("case", CONV_CASES[:6], ids=[c[0] for c in CONV_CASES[:6]])
-def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch):
+def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch, tune):
     """SPH3D_BWD_ALGO=1 selects the row-owned kernel of conv_bwd.cu everywhere: same results, and its
     grad_filter (fixed-order reduction of register partials) is bit-reproducible run to run"""
-    monkeypatch.setenv("SPH3D_BWD_ALGO", "1")
+    tune(SPH3D_BWD_ALGO="1")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(66, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
     ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
@@ -314,9 +320,9 @@ def test_depthwise_conv3d_backward_row_owned_form(case, pkg, oracle, monkeypatch
 
 
 @pytest.mark.parametrize("case", TRANSPOSE_CASES[:3], ids=[c[0] for c in TRANSPOSE_CASES[:3]])
-def test_transposed_backward_canonical_order_is_deterministic(case, pkg, oracle, monkeypatch):
-    monkeypatch.setenv("SPH3D_BWDT_SORT", "1")
-    monkeypatch.setenv("SPH3D_BWD_ALGO", "2")
+def test_transposed_backward_canonical_order_is_deterministic(case, pkg, oracle, monkeypatch, tune):
+    tune(SPH3D_BWDT_SORT="1")
+    tune(SPH3D_BWD_ALGO="2")
     x, W, idx, cnt, filt = _conv_inputs(oracle, case)
     go = features(66, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
     gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
