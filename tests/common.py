@@ -49,3 +49,23 @@ def assert_equal(a, b, what=""):
     neq = a != b
     assert not neq.any(), "%s: %d/%d elements differ (first at %s)" % (
         what, int(neq.sum()), neq.size, tuple(np.argwhere(neq)[0]))
+
+
+def assert_close_terms(new, truth, abs_terms, rtol=1e-5, what=""):
+    """ELEMENTWISE bound for a sum of products: |new - truth| <= rtol * (sum of the magnitudes of that element's own
+    summands) -- the backward-error form of "1e-5 relative fp32" (an fp32 sum of n terms is only accurate relative to
+    sum |terms|, never relative to a result that cancels).  abs_terms is the same op evaluated on |inputs|.
+    Returns (max error / abs_terms, max plain relative error over elements above 1e-3 of the scale) for reporting."""
+    new = np.asarray(new, dtype=np.float64)
+    truth = np.asarray(truth, dtype=np.float64)
+    abs_terms = np.asarray(abs_terms, dtype=np.float64)
+    assert new.shape == truth.shape == abs_terms.shape, (what, new.shape, truth.shape, abs_terms.shape)
+    err = np.abs(new - truth)
+    bad = err > rtol * abs_terms + 1e-30
+    worst = float(np.max(err / np.maximum(abs_terms, 1e-30))) if err.size else 0.0
+    scale = float(np.max(np.abs(truth))) if truth.size else 0.0
+    big = np.abs(truth) > 1e-3 * scale
+    rel = float(np.max(err[big] / np.abs(truth[big]))) if big.any() else 0.0
+    assert not bad.any(), "%s: %d/%d elements beyond %g x sum|terms| (worst %.3e; max plain relative error %.3e)" % (
+        what, int(bad.sum()), bad.size, rtol, worst, rel)
+    return worst, rel

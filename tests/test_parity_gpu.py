@@ -362,12 +362,12 @@ def test_plan_sharing_between_the_convolutions_of_a_level(pkg, oracle):
     o1 = pkg.tf_conv3d.depthwise_conv3d(xt, W1t, tidx, tcnt, tfilt)
     o2 = pkg.tf_conv3d.depthwise_conv3d(xt, W2t, tidx, tcnt, tfilt)
     (o1 * T(g1)).sum().backward(retain_graph=True)
-    plans = getattr(tfilt, "_sph3d_plans")
-    assert len(plans) == 1
-    plan_obj = next(iter(plans.values()))
+    bwd_plans = lambda: [v for k, v in getattr(tfilt, "_sph3d_plans").items() if k[0] == "bwd"]
+    assert len(bwd_plans()) == 1                                             # (the forward's sorted edge list sits beside it)
+    plan_obj = bwd_plans()[0]
     gx1 = xt.grad.clone(); xt.grad = None
     (o2 * T(g2)).sum().backward()
-    assert next(iter(tfilt._sph3d_plans.values())) is plan_obj              # reused, not rebuilt (C*r = 128: planned form)
+    assert len(bwd_plans()) == 1 and bwd_plans()[0] is plan_obj             # reused, not rebuilt (C*r = 128: planned form)
     assert_close(A(gx1), ti1, 1e-5, "shared plan: grad_input conv 1"); assert_close(A(W1t.grad), tf1, 1e-5, "grad_filter conv 1")
     assert_close(A(xt.grad), ti2, 1e-5, "shared plan: grad_input conv 2"); assert_close(A(W2t.grad), tf2, 1e-5, "grad_filter conv 2")
     # edit the graph in place: the stale plan must not be used
@@ -376,7 +376,7 @@ def test_plan_sharing_between_the_convolutions_of_a_level(pkg, oracle):
     ti3, tf3 = oracle.depthwise_conv3d_grad(x, W1, g1, idx, cnt2, filt)
     xt3 = T(x).requires_grad_(True); W3t = T(W1).requires_grad_(True)
     (pkg.tf_conv3d.depthwise_conv3d(xt3, W3t, tidx, tcnt, tfilt) * T(g1)).sum().backward()
-    assert next(iter(tfilt._sph3d_plans.values())) is not plan_obj
+    assert len(bwd_plans()) == 1 and bwd_plans()[0] is not plan_obj
     assert_close(A(xt3.grad), ti3, 1e-5, "rebuilt plan: grad_input"); assert_close(A(W3t.grad), tf3, 1e-5, "rebuilt plan: grad_filter")
 
 
