@@ -71,7 +71,7 @@ struct TGeom {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static TGeom t_geom(int B, int N, int M, int F, int K)
+static TGeom t_geom(int B, int N, int M, int F, int K, bool want_fold)
 {
     TGeom g{};
     g.ok = false;
@@ -101,7 +101,9 @@ static TGeom t_geom(int B, int N, int M, int F, int K)
     int cb = 1;
     while ((1 << cb) < K) cb++;
     const long long BM = (long long)B * M;
-    bool fold = BM <= (1LL << (32 - sb - cb));
+    // want_fold: the pool / unpool gather always folds (its scale is per edge); the convolution folds only on request
+    // (SPH3D_BWDT_FOLD=1): the extra staged word costs the gather kernel more than the scaled copy saves
+    bool fold = want_fold && BM <= (1LL << (32 - sb - cb));
     if (!fold) cb = 0;
     if (BM > (1LL << (32 - sb))) return g;
     g.sb = sb; g.cb = cb; g.fold = fold;
@@ -308,9 +310,13 @@ __device__ __forceinline__ void st_strip_smem(float* p, const float (&v)[VEC])
 // cloud together (the gathered cloud stays L2-resident), and the assignment is reproducible.
 // Per point the warp runs a three-stage software pipeline, two points ahead: segment boundaries (i+2), entry
 // list + input strip (i+1), gathers (i); inside a point 4*DEPTH feature-strip gathers are in flight.
-template <int VEC, int R, int THREADS, int DEPTH>
+// FOLD = false: `gs` is the pre-scaled copy grad_output / cnt with one zero row appended at row index `zrow` (the landing
+// row of the padding edges) and the segment sums are plain adds.  FOLD = true: `gs` is grad_output itself, every entry
+// carries nn_count - 1 of its row in cb bits and the sums are FMAs with 1/cnt (padding edges: scale 0); no scaled copy
+// is written, at the price of one more staged word per edge (measured slower at Cfg-T: DESIGN.md 4.3).
+template <int VEC, int R, int THREADS, int DEPTH, bool FOLD>
 __global__ void __launch_bounds__(THREADS, 1)
-conv_bwd_t_kernel(unsigned rows /* B*N */, int sb, int cb, int F, int C, int G, int SLOTS,
+conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow, int sb, int cb, int F, int C, int G, int SLOTS,
                   const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
                   const float* __restrict__ input, const float* __restrict__ filter,
                   float* __restrict__ grad_input, float* __restrict__ gw_partial)
@@ -347,6 +353,7 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, int sb, int cb, int F, int C, int G, 
     const unsigned gsStrideB = (unsigned)Co * 4u;
     const unsigned smask = (1u << sb) - 1u, cmask = (1u << cb) - 1u;
     const int sh = sb + cb;
+    const unsigned zoff = zrow * gsStrideB;              // FOLD = false: padding edges gather the zero row
     const char* gb = reinterpret_cast<const char*>(gs) + (size_t)i0ld * 4;
     const float* inl = input + i0ld / R;                 // my first input channel
     float* gil = grad_input + i0ld / R;
@@ -403,10 +410,14 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, int sb, int cb, int F, int C, int G, 
         for (int e = 0; e < VEC; e++) { gi[e] = 0.f; T[e] = 0.f; }
 
         auto consume = [&](const float (&v)[VEC], int code, float sc) {
-            float scv[VEC];
+            if constexpr (FOLD) {
+                float scv[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; e++) scv[e] = sc;
-            strip_fma<VEC>(T, v, scv);
+                for (int e = 0; e < VEC; e++) scv[e] = sc;
+                strip_fma<VEC>(T, v, scv);
+            } else {
+                strip_add<VEC>(T, v);
+            }
             if (code & 1) {                                // last edge of its bin segment (warp-uniform)
                 const int s = code >> 1;
                 float w[VEC], a[VEC];
@@ -426,13 +437,22 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, int sb, int cb, int F, int C, int G, 
         };
         auto consume4 = [&](int p, const float (&v)[4][VEC]) {
             const int4 cc = *reinterpret_cast<const int4*>(sCode + p);
-            const float4 ss = *reinterpret_cast<const float4*>(sScale + p);
+            float4 ss = make_float4(1.f, 1.f, 1.f, 1.f);
+            if constexpr (FOLD) ss = *reinterpret_cast<const float4*>(sScale + p);
             if (((cc.x | cc.y | cc.z | cc.w) & 1) == 0) {  // no segment ends inside this batch (the common case)
-                float s0[VEC], s1[VEC], s2[VEC], s3[VEC];
+                if constexpr (FOLD) {
+                    float s0[VEC], s1[VEC], s2[VEC], s3[VEC];
 #pragma unroll
-                for (int e = 0; e < VEC; e++) { s0[e] = ss.x; s1[e] = ss.y; s2[e] = ss.z; s3[e] = ss.w; }
-                strip_fma<VEC>(T, v[0], s0); strip_fma<VEC>(T, v[1], s1);
-                strip_fma<VEC>(T, v[2], s2); strip_fma<VEC>(T, v[3], s3);
+                    for (int e = 0; e < VEC; e++) { s0[e] = ss.x; s1[e] = ss.y; s2[e] = ss.z; s3[e] = ss.w; }
+                    strip_fma<VEC>(T, v[0], s0); strip_fma<VEC>(T, v[1], s1);
+                    strip_fma<VEC>(T, v[2], s2); strip_fma<VEC>(T, v[3], s3);
+                } else {
+                    float u[VEC], w2[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) { u[e] = v[0][e]; w2[e] = v[2][e]; }
+                    strip_add<VEC>(u, v[1]); strip_add<VEC>(w2, v[3]);
+                    strip_add<VEC>(T, u); strip_add<VEC>(T, w2);
+                }
             } else {
                 consume(v[0], cc.x, ss.x); consume(v[1], cc.y, ss.y); consume(v[2], cc.z, ss.z); consume(v[3], cc.w, ss.w);
             }
@@ -449,23 +469,24 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, int sb, int cb, int F, int C, int G, 
                 if (p1 < nt) e1 = __ldg(entries + kt + p1);
             }
             const int s0 = (int)(e0 & smask), s1 = (int)(e1 & smask);
-            // padding edges (tiles are rounded up to a multiple of four) gather the tile's first row with scale 0
-            const unsigned off_first = __shfl_sync(FULL_MASK, (e0 >> sh) * gsStrideB, 0);
+            // padding edges (tiles are rounded up to a multiple of four): FOLD gathers the tile's first row with scale 0
+            unsigned off_pad = zoff;
+            if constexpr (FOLD) off_pad = __shfl_sync(FULL_MASK, (e0 >> sh) * gsStrideB, 0);
             int nx0 = __shfl_down_sync(FULL_MASK, s0, 1);
             const int nx1 = __shfl_down_sync(FULL_MASK, s1, 1);
             const int first1 = __shfl_sync(FULL_MASK, s1, 0);
             if (lane == 31) nx0 = first1;
             if (p0 < nt4) {
                 const bool real = p0 < nt;
-                sOff[p0] = real ? (e0 >> sh) * gsStrideB : off_first;
+                sOff[p0] = real ? (e0 >> sh) * gsStrideB : off_pad;
                 sCode[p0] = real ? ((s0 << 1) | ((p0 == nt - 1 || nx0 != s0) ? 1 : 0)) : 0;
-                sScale[p0] = real ? (cb ? 1.0f / (float)(((e0 >> sb) & cmask) + 1u) : 1.0f) : 0.f;
+                if constexpr (FOLD) sScale[p0] = real ? 1.0f / (float)(((e0 >> sb) & cmask) + 1u) : 0.f;
             }
             if (p1 < nt4) {
                 const bool real = p1 < nt;
-                sOff[p1] = real ? (e1 >> sh) * gsStrideB : off_first;
+                sOff[p1] = real ? (e1 >> sh) * gsStrideB : off_pad;
                 sCode[p1] = real ? ((s1 << 1) | ((p1 == nt - 1 || nx1 != s1) ? 1 : 0)) : 0;
-                sScale[p1] = real ? (cb ? 1.0f / (float)(((e1 >> sb) & cmask) + 1u) : 1.0f) : 0.f;
+                if constexpr (FOLD) sScale[p1] = real ? 1.0f / (float)(((e1 >> sb) & cmask) + 1u) : 0.f;
             }
             __syncwarp();
             // software pipeline over batches of four gathers, 4*DEPTH strips in flight
@@ -612,6 +633,7 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * N * C, st);
     if (e != cudaSuccess) return (int)e;
     const float* gsrc = grad_output;
+    const unsigned zrow = (unsigned)((long long)B * M);
     if (!g.fold) {
         gsrc = gs;
         const int V = (Co % 4 == 0) ? 4 : ((Co % 2 == 0) ? 2 : 1);
@@ -627,10 +649,17 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     const unsigned rows = (unsigned)((long long)B * N);
 #define LAUNCH_T2(V, RR, TH, DP)                                                                                 \
     do {                                                                                                         \
-        e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP>, p.smem);                                                  \
-        if (e != cudaSuccess) return (int)e;                                                                     \
-        conv_bwd_t_kernel<V, RR, TH, DP><<<grid, TH, p.smem, st>>>(rows, g.sb, g.cb, F, C, g.G, g.SLOTS, seg, ent, gsrc, \
-                                                                   input, filter, grad_input, part);             \
+        if (g.fold) {                                                                                            \
+            e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP, true>, p.smem);                                        \
+            if (e != cudaSuccess) return (int)e;                                                                 \
+            conv_bwd_t_kernel<V, RR, TH, DP, true><<<grid, TH, p.smem, st>>>(rows, zrow, g.sb, g.cb, F, C, g.G, g.SLOTS, seg, ent, \
+                                                                             gsrc, input, filter, grad_input, part); \
+        } else {                                                                                                 \
+            e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP, false>, p.smem);                                       \
+            if (e != cudaSuccess) return (int)e;                                                                 \
+            conv_bwd_t_kernel<V, RR, TH, DP, false><<<grid, TH, p.smem, st>>>(rows, zrow, g.sb, g.cb, F, C, g.G, g.SLOTS, seg, ent, \
+                                                                              gsrc, input, filter, grad_input, part); \
+        }                                                                                                        \
     } while (0)
     const int depth = t_depth(p.threads / 32);
 #define LAUNCH_T(V, RR)                                                                                          \
@@ -667,12 +696,12 @@ bool bwd_transposed_supported(int B, int N, int M, int F, int C, int r, int K)
     if (algo == 1) return false;
     if (algo != 2 && r != 1) return false;
     TPlanMain p;
-    return t_plan_main(B, N, M, F, C, r, t_geom(B, N, M, F, K), &p);
+    return t_plan_main(B, N, M, F, C, r, t_geom(B, N, M, F, K, tunables().bwdt_fold == 1), &p);
 }
 
 size_t bwd_transposed_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
 {
-    const TGeom g = t_geom(B, N, M, F, K);
+    const TGeom g = t_geom(B, N, M, F, K, tunables().bwdt_fold == 1);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return 0;
     return g.total + t_work(B, M, F, C, r, g, p).total;
@@ -682,7 +711,7 @@ int bwd_transposed_run(int B, int N, int M, int F, int C, int r, int K, const in
                        const int* bin_index, const float* input, const float* filter, const float* grad_output,
                        float* grad_input, float* grad_filter, void* workspace, size_t workspace_bytes, cudaStream_t st)
 {
-    const TGeom g = t_geom(B, N, M, F, K);
+    const TGeom g = t_geom(B, N, M, F, K, tunables().bwdt_fold == 1);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return (int)cudaErrorInvalidValue;
     if (!workspace || workspace_bytes < g.total + t_work(B, M, F, C, r, g, p).total) return (int)cudaErrorInvalidValue;
@@ -753,7 +782,7 @@ t_gather_kernel(unsigned rows /* B*S */, int sh, int sb, unsigned cmask, int C, 
 // S = source points per cloud (rows of grad_input), R = referencing rows per cloud (rows of grad_output)
 static TGeom pool_geom(int B, int S, int R, int K)
 {
-    TGeom g = t_geom(B, S, R, 1, K);
+    TGeom g = t_geom(B, S, R, 1, K, true);
     if (g.ok && !g.fold) g.ok = false;                              // the scale code must ride in the entry
     if (g.ok && ((long long)B * R * 4 >= (1LL << 30))) g.ok = false;
     return g;
@@ -804,7 +833,7 @@ using namespace sph3d;
 
 extern "C" size_t sph3d_conv_transpose_bytes(int B, int N, int M, int F, int K)
 {
-    const TGeom g = t_geom(B, N, M, F, K);
+    const TGeom g = t_geom(B, N, M, F, K, tunables().bwdt_fold == 1);
     return g.ok ? g.total : 0;
 }
 
@@ -812,7 +841,7 @@ extern "C" int sph3d_conv_transpose(int B, int N, int M, int F, int K, const int
                                     const int* bin_index, void* plan, size_t plan_bytes, void* stream)
 {
     g_last_launch_count = 0;
-    const TGeom g = t_geom(B, N, M, F, K);
+    const TGeom g = t_geom(B, N, M, F, K, tunables().bwdt_fold == 1);
     if (!g.ok || !nn_index || !nn_count || !bin_index || !plan || plan_bytes < g.total) return (int)cudaErrorInvalidValue;
     int launches = 0;
     int rc = t_build_plan(B, N, M, F, K, g, nn_index, nn_count, bin_index, reinterpret_cast<char*>(plan),
@@ -823,7 +852,7 @@ extern "C" int sph3d_conv_transpose(int B, int N, int M, int F, int K, const int
 
 extern "C" size_t sph3d_depthwise_conv3d_grad_planned_workspace_bytes(int B, int N, int M, int F, int C, int r, int K)
 {
-    const TGeom g = t_geom(B, N, M, F, K);
+    const TGeom g = t_geom(B, N, M, F, K, tunables().bwdt_fold == 1);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return 0;
     return t_work(B, M, F, C, r, g, p).total;
@@ -835,7 +864,7 @@ extern "C" int sph3d_depthwise_conv3d_grad_planned(int B, int N, int M, int F, i
                                                    float* grad_filter, void* workspace, size_t workspace_bytes, void* stream)
 {
     g_last_launch_count = 0;
-    const TGeom g = t_geom(B, N, M, F, K);
+    const TGeom g = t_geom(B, N, M, F, K, tunables().bwdt_fold == 1);
     TPlanMain p;
     if (!t_plan_main(B, N, M, F, C, r, g, &p)) return (int)cudaErrorInvalidValue;
     if (!nn_count || !plan || plan_bytes < g.total || !input || !filter || !grad_output || !grad_input || !grad_filter ||

@@ -175,7 +175,7 @@ struct Tunables {
     int rows_per_chunk;                                  // SPH3D_ROWS_PER_CHUNK (pins the chunk size when set)
     int fwd_threads, fwd_vec;                            // SPH3D_FWD_THREADS, SPH3D_FWD_VEC
     int bwd_algo, bwd_vec, bwd_g, bwd_threads, bwd_cta_reduce;   // SPH3D_BWD_*  (row-owned backward)
-    int bwdt_threads, bwdt_depth, bwdt_g, bwdt_sort;     // SPH3D_BWDT_* (transposed backward)
+    int bwdt_threads, bwdt_depth, bwdt_g, bwdt_sort, bwdt_fold;   // SPH3D_BWDT_* (transposed backward)
     int nnquery_grid;                                    // SPH3D_NNQUERY_GRID: -1 unset, 0 never, 2 whenever possible
 };
 const Tunables& tunables();                              // conv_fwd.cu

@@ -48,6 +48,7 @@ static Tunables read_tunables()
     t.bwdt_depth = env_int("SPH3D_BWDT_DEPTH", 0);
     t.bwdt_g = env_int("SPH3D_BWDT_G", 0);
     t.bwdt_sort = env_int("SPH3D_BWDT_SORT", 0);
+    t.bwdt_fold = env_int("SPH3D_BWDT_FOLD", 0);
     t.nnquery_grid = env_int("SPH3D_NNQUERY_GRID", -1);
     return t;
 }

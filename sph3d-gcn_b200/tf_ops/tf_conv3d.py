@@ -22,7 +22,8 @@ def _forward(input, filter, nn_index, nn_count, bin_index, graph=None):
     B, N, C = input.shape
     F, _, r = filter.shape
     M, K = nn_index.shape[1], nn_index.shape[2]
-    if SHARE_PLANS and graph is not None and _lib.lib().sph3d_depthwise_conv3d_planned_supported(B, N, M, F, C, r, K):
+    if (SHARE_PLANS and FORWARD_PLANS and graph is not None
+            and _lib.lib().sph3d_depthwise_conv3d_planned_supported(B, N, M, F, C, r, K)):
         plan = _shared_plan("fwd", graph[0], graph[1], graph[2], F, N)
         if plan is not None:
             return depthwise_conv3d_planned(input, filter, nn_count, plan, K)
@@ -163,6 +164,10 @@ def depthwise_conv3d_grad_planned(input, filter, grad_output, nn_count, plan, nn
 # as an attribute of the bin_index tensor OBJECT (it lives and dies with the graph; in-place edits of an index tensor
 # change its _version and invalidate it).  With SHARE_PLANS off every call runs the one-call entry points.
 SHARE_PLANS = True
+# The forward's plan (per-row bin sort hoisted out of the kernel) is OFF by default: measured on B200 the in-kernel sort
+# costs the forward 5 % (0.589 -> 0.559 ms at Cfg-T) while writing the words costs 0.14 ms per graph, so two
+# convolutions per graph do not pay it back (profiles/r2_stage_a.json).  The entry points stay (C ABI + tests).
+FORWARD_PLANS = False
 _BUILDERS = {"fwd": lambda *a: conv_sort(*a), "bwd": lambda *a: conv_transpose(*a)}
 
 
@@ -185,15 +190,18 @@ def _shared_plan(kind, nn_index, nn_count, bin_index, num_bins, npoint):
 
 def emit_plans(nn_index, nn_count, bin_index, num_bins, npoint, backward=True):
     """build the graph-only plans of the convolution now (graph-build side) and hang them off bin_index"""
-    _shared_plan("fwd", nn_index, nn_count, bin_index, num_bins, npoint)
+    if FORWARD_PLANS:
+        _shared_plan("fwd", nn_index, nn_count, bin_index, num_bins, npoint)
     if backward:
         _shared_plan("bwd", nn_index, nn_count, bin_index, num_bins, npoint)
 
 
 def _use_planned(C, r):
-    """whether a shared plan pays for this layer: always for r = 1 (the one-call form transposes anyway); for r = 2 the
-    transposed form gathers C*r floats per edge and wins only for narrow layers"""
-    return r == 1 or (r == 2 and C * r <= 128)
+    """whether a shared plan pays for this layer.  r = 1: always (the one-call form transposes anyway).  r = 2: the
+    transposed form gathers C*r floats per edge where the row-owned one gathers C and reduces C; with the plan shared by
+    the level's two convolutions it measured faster at every S3DIS / Cfg-T shape (profiles/r2_stage_a.json: 2.03 vs
+    2.59 ms at C = 128, 0.25 vs 0.39 ms at C = 64), so it is used whenever the plan applies."""
+    return r in (1, 2)
 
 
 class _DepthwiseConv3d(torch.autograd.Function):

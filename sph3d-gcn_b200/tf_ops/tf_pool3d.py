@@ -27,8 +27,10 @@ def max_pool3d_grad(input, grad_output, max_index):
     return grad_input
 
 
-# True: the gradient transposes the graph and gathers (no atomics); False: vector-reduction scatter (csrc/pool3d.cu)
-GATHER_FORM_GRAD = True
+# True: the gradient transposes the graph and gathers (no atomics); False: vector-reduction scatter (csrc/pool3d.cu).
+# Measured (profiles/r2_stage_a.json): the gather form wins only for avg-pool at Cfg-T (0.38 vs 0.49 ms); at the S3DIS
+# shapes the transposition costs more than the reductions it saves, so the scatter form stays the default.
+GATHER_FORM_GRAD = False
 
 
 def avg_pool3d_grad(input, grad_output, nn_index, nn_count):

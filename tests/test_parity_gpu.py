@@ -233,9 +233,7 @@ def _plan_layout(B, N, M, F, K):
     sums_off = a256(nseg_pad * 4)
     ent_off = sums_off + a256(nseg_pad // 4096 * 4)
     sb = max(1, (SL - 1).bit_length())
-    cb = max(1, (K - 1).bit_length())
-    if B * M > (1 << (32 - sb - cb)):
-        cb = 0
+    cb = 0                                       # the 1/cnt code rides in the entries only with SPH3D_BWDT_FOLD=1
     return G, SL, FP, nseg, ent_off // 4, sb, cb
 
 

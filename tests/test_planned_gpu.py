@@ -44,7 +44,8 @@ def test_planned_forward_is_bit_identical(case, pkg, oracle, monkeypatch):
     for rep in range(2):
         planned = pkg.tf_conv3d.depthwise_conv3d_planned(tx, tW, tc, plan, idx.shape[2])
         assert_equal(A(planned), A(one_call), case[0] + " planned vs one-call forward")
-    through_op = pkg.tf_conv3d.depthwise_conv3d(tx, tW, ti, tc, tf)           # SHARE_PLANS: builds + caches the words
+    monkeypatch.setattr(pkg.tf_conv3d, "FORWARD_PLANS", True)
+    through_op = pkg.tf_conv3d.depthwise_conv3d(tx, tW, ti, tc, tf)           # SHARE_PLANS + FORWARD_PLANS: builds + caches the words
     assert any(k[0] == "fwd" for k in tf._sph3d_plans)
     assert_equal(A(through_op), A(one_call), case[0] + " op (shared plan) vs one-call forward")
     assert_close(A(planned), oracle.depthwise_conv3d(x, W, idx, cnt, filt, mode=1), 1e-5, case[0] + " planned vs oracle")
@@ -56,6 +57,7 @@ def test_spherical_kernel_emits_the_plans(pkg, oracle, monkeypatch):
     B, N, K, C = 2, 900, 32, 64
     xyz, q, radius, idx, cnt, dst, filt = _graph(oracle, 131, B, N, K)
     monkeypatch.setattr(pkg.tf_buildkernel, "EMIT_PLANS", "train")
+    monkeypatch.setattr(pkg.tf_conv3d, "FORWARD_PLANS", True)
     ti, tc, td = T(idx), T(cnt), T(dst)
     tfilt = pkg.tf_buildkernel.spherical_kernel(T(xyz), T(xyz), ti, tc, td, radius, kernel=[8, 2, 2])
     assert_equal(A(tfilt), filt)
@@ -67,7 +69,7 @@ def test_spherical_kernel_emits_the_plans(pkg, oracle, monkeypatch):
     out = pkg.tf_conv3d.depthwise_conv3d(xt, Wt, ti, tc, tfilt)
     assert L.sph3d_last_launch_count() == 1                                   # the gather kernel alone
     out.backward(T(go))
-    assert L.sph3d_last_launch_count() == 2                                   # gather pass + partial reduction
+    assert L.sph3d_last_launch_count() == 3                                   # scaled copy + gather pass + partial reduction
     assert len(tfilt._sph3d_plans) == 2
     assert_close(A(out), oracle.depthwise_conv3d(x, W, idx, cnt, filt, 1), 1e-5)
     gi, gf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
@@ -137,3 +139,15 @@ def test_interpolate_grad_forms(case, gather, pkg, oracle, monkeypatch):
         assert_close(A(pkg.tf_unpool3d.mean_interpolate_grad(T(x), T(go), T(idx), T(cnt))), want_m, 1e-5, name + " mean grad")
         assert_close(A(pkg.tf_unpool3d.weighted_interpolate_grad(T(x), T(go), T(w), T(idx), T(cnt))), want_w, 1e-5,
                      name + " weighted grad")
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[0] in ("c128_r1", "c64_r2", "k156_tiles")], ids=["c128_r1", "c64_r2", "k156_tiles"])
+def test_transposed_backward_with_folded_scale(case, pkg, oracle, tune):
+    """SPH3D_BWDT_FOLD=1: the plan entries carry nn_count, the gather kernel reads grad_output directly"""
+    tune(SPH3D_BWDT_FOLD="1", SPH3D_BWD_ALGO="2")
+    x, W, idx, cnt, filt = _conv_inputs(oracle, case)
+    cnt = cnt.copy(); cnt[:, 4::7] = np.maximum(cnt[:, 4::7] // 3, 1)
+    go = features(65, x.shape[0], idx.shape[1], x.shape[2] * W.shape[2])
+    ti, tf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
+    gi, gf = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_close(A(gi), ti, 1e-5, case[0] + " folded grad_input"); assert_close(A(gf), tf, 1e-5, case[0] + " folded grad_filter")
