@@ -1,27 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the SPH3D-GCN hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfgT|cfg1|s3dis_l1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload cfgT|cfgT_r2|s3dis_l1|cfg1|s3dis_model|modelnet_model|shapenet_model]
+                    [--scaling weak|strong]
 
-A "step" is one pass of the depthwise spherical convolution, forward + backward (grad_input and
-grad_filter), over one batch of synthetic point clouds -- BASELINE.json's metric
-("points/sec SPH3D conv fwd+bwd") on its headline shape Cfg-T: B=32 clouds x N=M=10000 points,
-K=64 neighbours, Cin=128, multiplier 1, 8x2x2+1 = 33 spherical bins.  Neighbour and bin indices
-come from this library's own (oracle-verified) ball query + spherical kernel on seeded uniform
-clouds with the saturating radius of BASELINE.md, so the graph has real spatial structure.
+Conv workloads (default cfgT).  A "step" is one pass of the depthwise spherical convolution, forward + backward
+(grad_input and grad_filter), over one batch of synthetic point clouds -- BASELINE.json's metric ("points/sec SPH3D conv
+fwd+bwd") on its headline shape Cfg-T: B=32 clouds x N=M=10000 points, K=64 neighbours, Cin=128, multiplier 1, 8x2x2+1 =
+33 spherical bins.  Neighbour and bin indices are the ball query + spherical kernel of seeded uniform clouds at the
+saturating radius of BASELINE.md (this library's, bit-identical to the reference's), so the graph has real structure.
 
-Prints ONE JSON line (rank 0).  `value` = whole-job points/s with inputs resident in HBM;
-`e2e` = the same metric through the public op (tf_conv3d.depthwise_conv3d -> ctypes -> C ABI) with
-every input coming from pinned HOST memory and every result read back, copies inside the timed region;
-`roofline` = algorithmic bytes / CUDA-event time of the dominant kernel vs MEASURED_PEAKS.json;
-`cpu_baseline` = the CPU oracle port (oracle/sph3d_oracle.c, OpenMP) on a bounded sample, rank 0, N=1;
-`ref_gpu` (extra) = the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same inputs, same GPU.
+  value     whole-job points/s, operands resident in HBM, through the reference-facing one-call ops
+            (sph3d_depthwise_conv3d / sph3d_depthwise_conv3d_grad): the gradient transposes the graph inside every step.
+  planned   the same step when the graph-build side has prepared the transposed graph (tf_conv3d.SHARE_PLANS, what the
+            model call graphs do: two convolutions per graph share one plan) + the cost of building that plan.
+  e2e       the same metric through the public op on HOST buffers: every step copies the features, the filter and the
+            incoming gradient from pinned host memory and reads all three results back; the graph tensors of the (static)
+            graph are resident, as their plan is.  Software-pipelined over three streams, double buffered.
+  roofline  algorithmic bytes / CUDA-event time of the dominant op vs MEASURED_PEAKS.json, plus the L2-path floor of the
+            gather that actually bounds it.
+  cpu_baseline  the CPU oracle port (oracle/sph3d_oracle.c, OpenMP) on a bounded sample, rank 0, N=1.
+  ref_gpu   (extra) the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same inputs, same GPU.
+  model     (extra, unless --no-extras) one SPH3D_s3dis training step (BASELINE.json configs[3], global B=8, N=8192) as a
+            CUDA graph, STRONG scaling over the ranks of this run (B/G clouds per rank), all gradients through bucketed
+            all-reduces that overlap the backward pass.
 
---impl reference: the reference's implementation of this path.  The reference has NO CPU kernels
-(every REGISTER_KERNEL_BUILDER is DEVICE_GPU), so its "own implementation" is its CUDA kernels:
-this arm runs oracle/_ref (unmodified tf_ops/*_gpu.cu, their <<<32,1024>>> launches, the glue's
-cudaMemset zero fills) on the GPU; if oracle/_ref did not travel it falls back to the CPU oracle port.
-Under torchrun only rank 0 works.
+Model workloads (*_model): value = points/s of whole training steps of the model call graph (forward + loss + backward
++ gradient all-reduce); --scaling strong splits the global batch over the ranks, weak gives every rank the full batch.
+
+--impl reference: the reference's implementation of the same path on the same config.  The reference has NO CPU kernels
+(every REGISTER_KERNEL_BUILDER is DEVICE_GPU), so its "own implementation" is its CUDA kernels: this arm runs oracle/_ref
+(unmodified tf_ops/*_gpu.cu, their <<<32,1024>>> launches, the glue's cudaMemset zero fills) on the GPU, builds its inputs
+with the reference's own ball query / bin kernels and never loads this library; if oracle/_ref did not travel it falls
+back to the CPU oracle port.  Under torchrun only rank 0 works.
 """
 import argparse
 import json
@@ -45,7 +57,11 @@ WORKLOADS = {
     "s3dis_l1": dict(B=8, N=8192, K=64, C=64, r=2, kernel=(8, 2, 2)),
     "cfg1": dict(B=2, N=1024, K=20, C=3, r=2, kernel=(8, 2, 2)),
 }
+MODEL_WORKLOADS = {"s3dis_model": "s3dis", "modelnet_model": "modelnet", "shapenet_model": "shapenet"}
+MODEL_SHAPE = {"modelnet": (32, 10000), "shapenet": (16, 2048), "s3dis": (8, 8192)}
 METRIC = "points/sec SPH3D conv fwd+bwd"
+MODEL_METRIC = "points/sec SPH3D model training step (fwd+loss+bwd+grad all-reduce)"
+L2_CAP_BYTES_PER_CLK = 6300.0          # measured LTS throughput cap (B300_MICROARCH.md "L2 cache"), B per SM-clock, whole chip
 
 
 def saturating_radius(N, K):
@@ -101,8 +117,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(inside), "reasons": sorted(reasons)}
 
 
-def make_inputs(cfg, seed, dev, S):
-    """seeded synthetic clouds -> graph (this library's nnquery + buildkernel) -> conv operands, on `dev`."""
+def bind_to_gpu_numa_node(index):
+    """run this process (and first-touch its pinned host buffers) on the CPUs NVML reports as local to GPU `index`"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus" % len(cpus)
+    except Exception as e:
+        return "unavailable:%s" % type(e).__name__
+    return "unavailable"
+
+
+def host_operands(cfg, seed):
+    """seeded synthetic clouds + conv operands on the host (shared by both arms: same seed -> same tensors)"""
     B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
     n, p, q = cfg["kernel"]
     F = n * p * q + 1
@@ -111,11 +144,28 @@ def make_inputs(cfg, seed, dev, S):
     x = torch.randn(B, N, C, generator=g, dtype=torch.float32)
     W = 0.1 * torch.randn(F, C, r, generator=g, dtype=torch.float32)
     go = torch.randn(B, N, C * r, generator=g, dtype=torch.float32)
-    radius = saturating_radius(N, K)
-    xyz_d = xyz.to(dev)
-    idx, cnt, dst = S.tf_nnquery.build_sphere_neighbor(xyz_d, xyz_d, radius=radius, nnsample=K)
+    return dict(xyz=xyz, x=x, W=W, go=go), saturating_radius(N, K), F
+
+
+def make_inputs(cfg, seed, dev, S):
+    """native arm: graph from this library's nnquery + buildkernel (bit-identical to the reference's) -> host dict"""
+    host, radius, F = host_operands(cfg, seed)
+    n, p, q = cfg["kernel"]
+    xyz_d = host["xyz"].to(dev)
+    idx, cnt, dst = S.tf_nnquery.build_sphere_neighbor(xyz_d, xyz_d, radius=radius, nnsample=cfg["K"])
     filt = S.tf_buildkernel.spherical_kernel(xyz_d, xyz_d, idx, cnt, dst, radius, kernel=[n, p, q])
-    host = dict(x=x, W=W, go=go, idx=idx.cpu(), cnt=cnt.cpu(), filt=filt.cpu(), xyz=xyz)
+    host.update(idx=idx.cpu(), cnt=cnt.cpu(), filt=filt.cpu())
+    return host, radius, F
+
+
+def make_inputs_reference(cfg, seed, dev, R):
+    """reference arm: the same operands, graph from the reference's OWN ball query + bin kernels (oracle/_ref)"""
+    host, radius, F = host_operands(cfg, seed)
+    n, p, q = cfg["kernel"]
+    xyz_d = host["xyz"].to(dev)
+    idx, cnt, dst = R.build_sphere_neighbor(xyz_d, xyz_d, radius, None, cfg["K"])
+    filt = R.spherical_kernel(xyz_d, xyz_d, idx, cnt, dst, radius, [n, p, q])
+    host.update(idx=idx.cpu(), cnt=cnt.cpu(), filt=filt.cpu())
     return host, radius, F
 
 
@@ -123,6 +173,17 @@ def algorithmic_bytes(B, N, M, C, r, F, E):
     fwd = 4 * (B * N * C + B * M * C * r + 2 * E + B * M + F * C * r)
     bwd = 4 * (B * M * C * r + 2 * B * N * C + 2 * E + B * M + 2 * F * C * r)
     return fwd, bwd
+
+
+def conv_config(workload, cfg, F, radius, E, world, scaling):
+    """the `config` object of a conv workload -- ONE function for both arms, so their keys and values coincide"""
+    B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
+    ab_fwd, ab_bwd = algorithmic_bytes(B, N, N, C, r, F, E)
+    return {"workload": workload, "B_per_gpu": B, "N": N, "M": N, "K": K, "Cin": C, "multiplier": r, "bins": F,
+            "radius": radius, "mean_neighbors": E / (B * N), "parallelism": "dp%d" % world, "scaling": scaling,
+            "l2": "inputs (%.0f MB/step) larger than L2, no flush" % ((ab_fwd + ab_bwd) / 2e6),
+            "e2e_feed": "features + filter + incoming gradient from pinned host memory every step, 3 results read back; "
+                        "the static graph's index tensors are resident"}
 
 
 def ncu_traffic(kernel_key):
@@ -182,111 +243,296 @@ def ref_gpu_times(dev_in, cfg, F, iters=2):
     return res
 
 
+class E2EPipeline(object):
+    """host-fed steps, software-pipelined over three streams with double buffering: H2D of step i+1 and D2H of step i-1
+    overlap the kernels of step i (PCIe is full duplex).  `compute(buffers) -> results` runs on the current stream."""
+
+    def __init__(self, pin, names, result_shapes, compute, requires_grad=()):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.pin, self.names, self.compute = pin, names, compute
+        self.s_comp, self.s_h2d, self.s_d2h = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        self.dbuf = [{k: torch.empty(pin[k].shape, dtype=pin[k].dtype, device=dev) for k in names} for _ in range(2)]
+        for bset in self.dbuf:
+            for k in requires_grad:
+                bset[k].requires_grad_(True)
+        self.hbuf = [[torch.empty(s, dtype=torch.float32).pin_memory() for s in result_shapes] for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]        # inputs of buffer b are on the device
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]      # kernels that read buffer b are done
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]       # results of buffer b are on the host
+        for e_ in self.ev_free + self.ev_out:
+            e_.record(self.s_comp)
+        self.h2d = sum(pin[k].numel() * pin[k].element_size() for k in names)
+        self.d2h = sum(t.numel() * t.element_size() for t in self.hbuf[0])
+
+    def step(self, i):
+        b = i & 1
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(self.ev_free[b])
+            with torch.no_grad():
+                for k in self.names:
+                    self.dbuf[b][k].copy_(self.pin[k], non_blocking=True)
+            self.ev_in[b].record(self.s_h2d)
+        self.s_comp.wait_event(self.ev_in[b])
+        self.s_comp.wait_event(self.ev_out[b])                     # result buffers of slot b (if reused) have left the device
+        res = self.compute(self.dbuf[b])
+        self.ev_free[b].record(self.s_comp)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_free[b])
+            self.s_d2h.wait_event(self.ev_out[b])                  # host buffer b was consumed two steps ago
+            for hdst, src in zip(self.hbuf[b], res):
+                src.record_stream(self.s_d2h)
+                hdst.copy_(src, non_blocking=True)
+            self.ev_out[b].record(self.s_d2h)
+
+    def drain(self):
+        self.s_comp.wait_event(self.ev_out[0]); self.s_comp.wait_event(self.ev_out[1])
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
 def run_reference_arm(args):
-    """--impl reference (rank 0 only)."""
+    """--impl reference (rank 0 only).  Never imports sph3d_gcn_b200 for the conv workloads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload in MODEL_WORKLOADS:
+        return run_reference_model(args)
     cfg = WORKLOADS[args.workload]
     B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
-    line = {"impl": "reference", "metric": METRIC, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, **{k: cfg[k] for k in ("B", "N", "K", "C", "r")}}}
-    import sph3d_gcn_b200 as S
-    import ref_gpu as R
-    use_gpu = torch.cuda.is_available() and R.available() and not args.reference_cpu
-    if torch.cuda.is_available():
-        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-        torch.cuda.set_device(dev)
-        host, radius, F = make_inputs(cfg, 1234 + 2, dev, S)
-    else:
-        line["unavailable"] = "no CUDA device: inputs for this workload are built with the GPU ball query"
-        print(json.dumps(line)); return
     M = N
-    if use_gpu:
-        pin = {k: v.pin_memory() for k, v in host.items() if k != "xyz"}
-        d = {k: v.to(dev) for k, v in pin.items()}
-        out = torch.empty(B, M, C * r, device=dev); gi = torch.empty(B, N, C, device=dev); gf = torch.empty(F, C, r, device=dev)
-        h_out, h_gi, h_gf = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out, gi, gf))
-
-        def step():
-            out.zero_(); R.launch_raw("conv", B, N, M, C, r, K, d["idx"], d["cnt"], d["filt"], d["x"], d["W"], out)
-            gi.zero_(); gf.zero_()
-            R.launch_raw("conv_grad", B, N, M, F, C, r, K, d["idx"], d["cnt"], d["filt"], d["x"], d["W"], d["go"], gi, gf)
-
-        # e2e gets the SAME treatment as the native arm: double-buffered operands/results, copies on side
-        # streams overlapping the (legacy-default-stream) reference kernels of the neighbouring steps
-        names = ("x", "W", "go", "idx", "cnt", "filt")
-        s_comp, s_h2d, s_d2h = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
-        dbuf = [{k: torch.empty_like(d[k]) for k in names} for _ in range(2)]
-        obuf = [[torch.empty_like(out), torch.empty_like(gi), torch.empty_like(gf)] for _ in range(2)]
-        hbuf = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out, gi, gf)] for _ in range(2)]
-        ev_in, ev_free, ev_out = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
-        for e_ in ev_free + ev_out:
-            e_.record(s_comp)
-        step_no = [0]
-
-        def step_e2e():
-            b = step_no[0] & 1
-            step_no[0] += 1
-            with torch.cuda.stream(s_h2d):
-                s_h2d.wait_event(ev_free[b])
-                for k in names:
-                    dbuf[b][k].copy_(pin[k], non_blocking=True)
-                ev_in[b].record(s_h2d)
-            s_comp.wait_event(ev_in[b]); s_comp.wait_event(ev_out[b])
-            q, (o_, gi_, gf_) = dbuf[b], obuf[b]
-            o_.zero_(); R.launch_raw("conv", B, N, M, C, r, K, q["idx"], q["cnt"], q["filt"], q["x"], q["W"], o_)
-            gi_.zero_(); gf_.zero_()
-            R.launch_raw("conv_grad", B, N, M, F, C, r, K, q["idx"], q["cnt"], q["filt"], q["x"], q["W"], q["go"], gi_, gf_)
-            ev_free[b].record(s_comp)
-            with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(ev_free[b])
-                for hdst, src in zip(hbuf[b], obuf[b]):
-                    hdst.copy_(src, non_blocking=True)
-                ev_out[b].record(s_d2h)
-        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))       # bounded: these kernels are slow
-        for _ in range(warm):
-            step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            step()
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        step_e2e(); step_e2e(); torch.cuda.synchronize()
-        e0.record()
-        for _ in range(steps):
-            step_e2e()
-        s_comp.wait_event(ev_out[0]); s_comp.wait_event(ev_out[1])
-        e1.record(); torch.cuda.synchronize()
-        ms_e2e = e0.elapsed_time(e1) / steps
-        h2d = sum(pin[k].numel() * pin[k].element_size() for k in ("x", "W", "go", "idx", "cnt", "filt"))
-        d2h = sum(t.numel() * t.element_size() for t in (out, gi, gf))
-        line.update(value=B * M / (ms * 1e-3), ms_per_step=ms, steps=steps, warmup=warm, gpu_launches=0,
-                    e2e={"value": B * M / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                    cpu_baseline={"value": B * M / (ms * 1e-3), "unit": "points/s", "cores": 0, "kind": "reference",
-                                  "sample": "UNMODIFIED reference CUDA kernels (oracle/_ref) on the GPU: the reference has no CPU "
-                                            "implementation of this path; full workload, %d steps" % steps})
-    else:
-        cb = cpu_baseline(host, cfg, target_seconds=20.0)
+    line = {"impl": "reference", "metric": METRIC, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic"}
+    import ref_gpu as R
+    if not torch.cuda.is_available():
+        line["unavailable"] = "no CUDA device: the reference implements this path on the GPU only"
+        print(json.dumps(line)); return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    use_gpu = R.available() and not args.reference_cpu
+    if not use_gpu:                                           # CPU oracle port on a bounded sample; graph from the port too
+        import oracle as O
+        O.build()
+        host, radius, F = host_operands(cfg, 1234 + 2)
+        nb = min(B, 2)
+        xyz = host["xyz"][:nb].numpy()
+        idx, cnt, dst = O.build_sphere_neighbor(xyz, xyz, radius, None, K)
+        filt = O.spherical_kernel(xyz, xyz, idx, cnt, dst, radius, list(cfg["kernel"]))
+        sub = dict(cfg, B=nb)
+        h2 = {k: host[k][:nb] for k in ("x", "go")}
+        h2.update(W=host["W"], idx=torch.from_numpy(idx), cnt=torch.from_numpy(cnt), filt=torch.from_numpy(filt))
+        cb = cpu_baseline(h2, sub, target_seconds=20.0)
+        E = int(cnt.sum()) * B // nb
         line.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb, gpu_launches=0,
+                    config=conv_config(args.workload, cfg, F, radius, E, args.gpus, args.scaling),
                     e2e={"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line)); return
+
+    host, radius, F = make_inputs_reference(cfg, 1234 + 2, dev, R)
+    E = int(host["cnt"].sum().item())
+    pin = {k: v.pin_memory() for k, v in host.items() if k != "xyz"}
+    d = {k: v.to(dev) for k, v in pin.items()}
+    out = torch.empty(B, M, C * r, device=dev); gi = torch.empty(B, N, C, device=dev); gf = torch.empty(F, C, r, device=dev)
+    KERNELS_PER_STEP = 3          # depthwise_conv3d_forward + depthwise_input_backward + depthwise_filter_backward (one smem window)
+
+    def step():
+        out.zero_(); R.launch_raw("conv", B, N, M, C, r, K, d["idx"], d["cnt"], d["filt"], d["x"], d["W"], out)
+        gi.zero_(); gf.zero_()
+        R.launch_raw("conv_grad", B, N, M, F, C, r, K, d["idx"], d["cnt"], d["filt"], d["x"], d["W"], d["go"], gi, gf)
+
+    obuf = [[torch.empty_like(out), torch.empty_like(gi), torch.empty_like(gf)] for _ in range(2)]
+    flip = [0]
+
+    def compute(q):                                           # same feed as the native arm: features per step, graph resident
+        o_, gi_, gf_ = obuf[flip[0] & 1]
+        flip[0] += 1
+        o_.zero_(); R.launch_raw("conv", B, N, M, C, r, K, d["idx"], d["cnt"], d["filt"], q["x"], q["W"], o_)
+        gi_.zero_(); gf_.zero_()
+        R.launch_raw("conv_grad", B, N, M, F, C, r, K, d["idx"], d["cnt"], d["filt"], q["x"], q["W"], q["go"], gi_, gf_)
+        return o_, gi_, gf_
+
+    pipe = E2EPipeline(pin, ("x", "W", "go"), [tuple(out.shape), tuple(gi.shape), tuple(gf.shape)], compute)
+    steps, warm = args.steps, args.warmup
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    for i in range(2):
+        pipe.step(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        pipe.step(i)
+    pipe.drain()
+    e1.record(); torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / steps
+    line.update(value=B * M / (ms * 1e-3), ms_per_step=ms, gpu_launches=KERNELS_PER_STEP * steps,
+                config=conv_config(args.workload, cfg, F, radius, E, args.gpus, args.scaling),
+                e2e={"value": B * M / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+                     "h2d_bytes_per_step": pipe.h2d, "d2h_bytes_per_step": pipe.d2h},
+                cpu_baseline={"value": B * M / (ms * 1e-3), "unit": "points/s", "cores": 0, "kind": "reference",
+                              "sample": "UNMODIFIED reference CUDA kernels (oracle/_ref) on the GPU: the reference has no CPU "
+                                        "implementation of this path; full workload, %d steps" % steps})
     print(json.dumps(line))
 
 
+def run_reference_model(args):
+    """whole-network step with every custom op swapped for the unmodified reference kernel (oracle/ref_model.py)"""
+    model = MODEL_WORKLOADS[args.workload]
+    B0, N = MODEL_SHAPE[model]
+    world = max(1, args.gpus)
+    B = B0 if args.scaling == "weak" else max(1, B0 // world)
+    line = {"impl": "reference", "metric": MODEL_METRIC, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": model_config(args.workload, model, B0, N, world, args.scaling)}
+    import ref_gpu as R
+    if not (torch.cuda.is_available() and R.available()):
+        line["unavailable"] = "oracle/_ref or the GPU is missing: the reference's graph ops exist as CUDA kernels only"
+        print(json.dumps(line)); return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    import sph3d_gcn_b200 as S                                 # host-side call graph only: every op below is the reference kernel
+    import ref_model
+    ref_model.install(S)
+    step, cfg, _ = S.utils.train_step.make_step(B, N, 7, model)
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    v = B * N / (ms * 1e-3)                                    # one rank's share of the (strong-scaled) batch; ranks are independent
+    line.update(value=v * world, ms_per_step=ms, steps=steps,
+                warmup=warm, gpu_launches=None,
+                e2e={"value": v * world, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                cpu_baseline={"value": v * world, "unit": "points/s", "cores": 0, "kind": "reference",
+                              "sample": "model call graph with every custom op = unmodified reference CUDA kernel, eager; rank 0 "
+                                        "times B=%d of the global batch and the figure assumes ideal scaling over %d ranks" % (B, world)})
+    print(json.dumps(line))
+
+
+def model_config(workload, model, B0, N, world, scaling):
+    return {"workload": workload, "model": "SPH3D_" + model, "global_batch": B0 * (world if scaling == "weak" else 1),
+            "B_per_gpu": B0 if scaling == "weak" else max(1, B0 // world), "N": N, "parallelism": "dp%d" % world,
+            "scaling": scaling, "l2": "activations of a step exceed L2, no flush",
+            "e2e_feed": "point clouds + labels from pinned host memory every step, loss read back"}
+
+
+# ------------------------------------------------------------------------------------------------- model steps
+def model_step_bench(S, model, B_global, N, world, rank, scaling, steps, warmup, dist, n_buckets=4):
+    """training steps of a model call graph as ONE CUDA graph per rank, gradients in flat buckets whose all-reduces overlap
+    the backward pass -> dict(ms_per_step, points_per_s, ...).  Falls back to a post-step flat all-reduce when NCCL cannot
+    be captured, and says which."""
+    du, gs, ts, u = S.utils.dist_util, S.utils.graph_step, S.utils.train_step, S.sph3gcn_util
+    B = B_global if scaling == "weak" else B_global // world
+    if B < 1:
+        return {"skipped": "global batch %d < %d ranks (replicas only beyond B ranks)" % (B_global, world)}
+    S.tf_conv3d.SHARE_PLANS = True
+    step, cfg, (pts, label, inner) = ts.make_step(B, N, 7 + rank, model)
+    step()                                                     # creates the variables
+    params = list(u.trainable_variables())
+    if world > 1:                                              # identical weights on every rank
+        for p in params:
+            dist.broadcast(p.data, 0)
+    buckets = du.GradBuckets(params, n_buckets=n_buckets, average=True)
+    step.set_zero_grads(buckets.zero)
+    mode = "graph+overlapped buckets"
+
+    def full():
+        out = step()
+        buckets.finish()
+        return out
+    try:
+        run = gs.GraphedStep(full, params, warmup=2)
+        run(); torch.cuda.synchronize()
+    except Exception as e:                                     # NCCL not capturable here: graph the step, reduce after it
+        mode = "graph + post-step flat all-reduce (%s)" % type(e).__name__
+        buckets.close()
+        torch.cuda.synchronize()
+        flat = du.GradBuckets(params, n_buckets=1, average=True)
+        flat.close()                                           # no hooks: reduce explicitly
+        step.set_zero_grads(flat.zero)
+        graphed = gs.GraphedStep(step, params, warmup=2)
+
+        def run():
+            out = graphed()
+            flat.pending = [1]
+            flat.finish()
+            return out
+        buckets = flat
+    for _ in range(warmup):
+        run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pred, end, loss = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    # host-fed variant: the batch (points, labels) comes from pinned host memory every step, the loss goes back
+    pin = [t.cpu().pin_memory() for t in (pts, label) + ((inner,) if inner is not None else ())]
+    dst = [pts, label] + ([inner] if inner is not None else [])
+    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def fed():
+        for h, dd in zip(pin, dst):
+            dd.copy_(h, non_blocking=True)
+        out = run()
+        hloss.copy_(out[2].detach(), non_blocking=True)
+    fed(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(steps):
+        fed()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_fed = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms_fed], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_fed = float(t)
+    grads_ok = bool(all(p.grad is not None and torch.isfinite(p.grad).all() for p in params))
+    return {"model": "SPH3D_" + model, "scaling": scaling, "global_batch": B * world, "B_per_gpu": B, "N": N, "n_gpus": world,
+            "ms_per_step": ms, "points_per_s": world * B * N / (ms * 1e-3),
+            "e2e_ms_per_step": ms_fed, "e2e_points_per_s": world * B * N / (ms_fed * 1e-3),
+            "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in pin), "d2h_bytes_per_step": 4,
+            "allreduce_bytes_per_step": buckets.flat.numel() * 4 if world > 1 else 0, "allreduce_buckets": len(buckets.bounds),
+            "execution": mode, "loss": float(loss.detach()), "all_grads_finite": grads_ok, "n_params": len(params)}
+
+
+# ------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfgT", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfgT", choices=sorted(WORKLOADS) + sorted(MODEL_WORKLOADS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="conv workloads: weak (every rank owns B clouds); model workloads default to strong (global batch / ranks)")
     ap.add_argument("--reference-cpu", action="store_true", help="--impl reference: force the CPU oracle port")
-    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / ref_gpu legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cpu_baseline / ref_gpu / model legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    is_model = args.workload in MODEL_WORKLOADS
+    if args.scaling is None:
+        args.scaling = "strong" if is_model else "weak"
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -294,13 +540,12 @@ def main():
 
     import torch.distributed as dist
     import sph3d_gcn_b200 as S
-    from importlib import import_module
-    dist_util = import_module("sph3d_gcn_b200.utils.dist_util")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    numa = bind_to_gpu_numa_node(local)
     sampler = ClockSampler(local)
     sampler.start()
     dev = torch.device("cuda", local)
@@ -310,9 +555,39 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
-    # every step pays the whole backward, graph transposition included: the steps reuse one graph, and a plan kept
-    # from step to step (tf_conv3d.SHARE_PLANS, meant for the two convolutions of a level) would be skipped work
-    S.tf_conv3d.SHARE_PLANS = False
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    if is_model:
+        model = MODEL_WORKLOADS[args.workload]
+        B0, N = MODEL_SHAPE[model]
+        wall0 = time.perf_counter()
+        rec = model_step_bench(S, model, B0, N, world, rank, args.scaling, args.steps, args.warmup, dist)
+        clocks = sampler.result(wall0, time.perf_counter())
+        if rank == 0:
+            line = {"metric": MODEL_METRIC, "value": rec.get("points_per_s"), "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": rec.get("ms_per_step"), "higher_is_better": True, "scaling": args.scaling,
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": model_config(args.workload, model, B0, N, world, args.scaling), "clocks": clocks,
+                    "e2e": {"value": rec.get("e2e_points_per_s"), "unit": "points/s", "ms_per_step": rec.get("e2e_ms_per_step"),
+                            "h2d_bytes_per_step": rec.get("h2d_bytes_per_step"), "d2h_bytes_per_step": rec.get("d2h_bytes_per_step")},
+                    "gpu_launches": None, "model": rec, "host_numa_binding": numa}
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------------------------------ conv workloads
+    C3 = S.tf_conv3d
     cfg = WORKLOADS[args.workload]
     B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
     M = N
@@ -321,174 +596,149 @@ def main():
     d = {k: v.to(dev) for k, v in pin.items()}
     E = int(d["cnt"].sum().item())
     L = S._lib.lib()
-
     x = d["x"].clone().requires_grad_(True)
     Wp = d["W"].clone().requires_grad_(True)
+    buckets = S.utils.dist_util.GradBuckets([Wp], n_buckets=1, average=False)     # grad_filter: flat storage, hook-driven all-reduce
 
     def step(timers=None):
-        """one hot-path pass through the public op: forward, backward, DP all-reduce of the weight gradient"""
-        x.grad = None; Wp.grad = None
+        """one hot-path pass through the public op: forward, backward (+ DP all-reduce of the weight gradient)"""
+        x.grad = None
+        buckets.zero()
         if timers: timers[0].record()
-        out = S.tf_conv3d.depthwise_conv3d(x, Wp, d["idx"], d["cnt"], d["filt"])
+        out = C3.depthwise_conv3d(x, Wp, d["idx"], d["cnt"], d["filt"])
         if timers: timers[1].record()
         out.backward(d["go"])
         if timers: timers[2].record()
-        dist_util.allreduce_gradients([Wp.grad])
+        buckets.finish()
         return out
 
-    def step_e2e(h):
-        for k in ("x", "W", "go", "idx", "cnt", "filt"):
-            d[k].copy_(pin[k], non_blocking=True)
-        with torch.no_grad():
-            x.copy_(d["x"]); Wp.copy_(d["W"])
-        out = step()
-        h[0].copy_(out.detach(), non_blocking=True); h[1].copy_(x.grad, non_blocking=True); h[2].copy_(Wp.grad, non_blocking=True)
+    def timed(nsteps, with_timers=True):
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(nsteps)]
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        t0.record()
+        for i in range(nsteps):
+            step(ev[i] if with_timers else None)
+        t1.record()
+        barrier()
+        wall1 = time.perf_counter()
+        ms = max_over_ranks(t0.elapsed_time(t1)) / nsteps
+        fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in ev])) if with_timers else None
+        bwd = float(np.mean([e[1].elapsed_time(e[2]) for e in ev])) if with_timers else None
+        return ms, fwd, bwd, wall0, wall1
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- value: every step pays the whole backward, graph transposition included (one-call entry points) -----------
+    C3.SHARE_PLANS = False
     for _ in range(args.warmup):
         step()
     launches_per_step = 0
-    S.tf_conv3d._forward(d["x"], d["W"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
-    S.tf_conv3d.depthwise_conv3d_grad(d["x"], d["W"], d["go"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
-
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    t0.record()
-    for i in range(args.steps):
-        step(ev[i])
-    t1.record()
-    barrier()
-    clocks = sampler.result(wall0, time.perf_counter())
-    ms_total = t0.elapsed_time(t1)
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    if world > 1:
-        tt = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
-    ms_step = ms_total / args.steps
+    C3._forward(d["x"], d["W"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
+    C3.depthwise_conv3d_grad(d["x"], d["W"], d["go"], d["idx"], d["cnt"], d["filt"]); launches_per_step += L.sph3d_last_launch_count()
+    ms_step, fwd_ms, bwd_ms, wall0, wall1 = timed(args.steps)
+    clocks = sampler.result(wall0, wall1)
     value = world * B * M / (ms_step * 1e-3)
 
-    # ---- end-to-end: host buffers in, results out, EVERY step ---------------------------------------
-    # Every step copies all six operands from pinned host memory and copies all three results back.  The
-    # steps are software-pipelined over three streams with double buffering (H2D of step i+1 and D2H of
-    # step i-1 overlap the kernels of step i; PCIe is full duplex), which is how a host-fed pipeline runs.
-    e2e_steps = args.steps
-    s_comp, s_h2d, s_d2h = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    names = ("x", "W", "go", "idx", "cnt", "filt")
-    dbuf = [{k: torch.empty_like(d[k]) for k in names} for _ in range(2)]
-    for bset in dbuf:
-        bset["x"].requires_grad_(True); bset["W"].requires_grad_(True)
-    hbuf = [[torch.empty(B, M, C * r).pin_memory(), torch.empty(B, N, C).pin_memory(), torch.empty(F, C, r).pin_memory()]
-            for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]        # inputs of buffer b are on the device
-    ev_free = [torch.cuda.Event() for _ in range(2)]      # kernels that read buffer b are done
-    ev_out = [torch.cuda.Event() for _ in range(2)]       # results of buffer b are on the host
-    for e_ in ev_free + ev_out:
-        e_.record(s_comp)
+    # ---- planned: the graph-build side prepared the transposed graph (what the model call graphs do) ---------------
+    C3.SHARE_PLANS = True
+    planned = {}
+    try:
+        plan = C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N)
+        if plan is not None:
+            for _ in range(3):
+                step()                                             # first backward builds + caches the plan on d["filt"]
+            p_ms, p_fwd, p_bwd, _, _ = timed(args.steps)
 
-    def e2e_step(i):
-        b = i & 1
-        with torch.cuda.stream(s_h2d):
-            s_h2d.wait_event(ev_free[b])
-            with torch.no_grad():
-                for k in names:
-                    dbuf[b][k].copy_(pin[k], non_blocking=True)
-            ev_in[b].record(s_h2d)
-        s_comp.wait_event(ev_in[b])
-        xb, Wb = dbuf[b]["x"], dbuf[b]["W"]
+            def _t(fn, n=10):
+                fn(); torch.cuda.synchronize()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b_.record(); torch.cuda.synchronize()
+                return a.elapsed_time(b_) / n
+            plan_ms = _t(lambda: C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N))
+            planned = {"value": world * B * M / (p_ms * 1e-3), "unit": "points/s", "ms_per_step": p_ms, "conv_fwd_ms": p_fwd,
+                       "conv_bwd_ms": p_bwd, "plan_build_ms": plan_ms,
+                       "value_plan_shared_by_2_convs": world * B * M / ((p_ms + plan_ms / 2) * 1e-3),
+                       "what": "same step with the transposed graph built once per graph on the graph-build side "
+                               "(tf_conv3d.SHARE_PLANS; the reference's models run two convolutions per graph)"}
+    except Exception as e:
+        planned = {"error": repr(e)}
+
+    # ---- end-to-end: host buffers in, results out, EVERY step (static graph resident, plan shared) -----------------
+    def compute(q):
+        xb, Wb = q["x"], q["W"]
         xb.grad = None; Wb.grad = None
-        out = S.tf_conv3d.depthwise_conv3d(xb, Wb, dbuf[b]["idx"], dbuf[b]["cnt"], dbuf[b]["filt"])
-        out.backward(dbuf[b]["go"])
-        dist_util.allreduce_gradients([Wb.grad])
-        ev_free[b].record(s_comp)
-        res = (out.detach(), xb.grad, Wb.grad)
-        with torch.cuda.stream(s_d2h):
-            s_d2h.wait_event(ev_free[b])
-            s_d2h.wait_event(ev_out[b])                     # host buffer b was consumed two steps ago
-            for hdst, src in zip(hbuf[b], res):
-                src.record_stream(s_d2h)
-                hdst.copy_(src, non_blocking=True)
-            ev_out[b].record(s_d2h)
-
+        out = C3.depthwise_conv3d(xb, Wb, d["idx"], d["cnt"], d["filt"])
+        out.backward(q["go"])
+        S.utils.dist_util.allreduce_gradients([Wb.grad])
+        return out.detach(), xb.grad, Wb.grad
+    pipe = E2EPipeline(pin, ("x", "W", "go"), [(B, M, C * r), (B, N, C), (F, C, r)], compute, requires_grad=("x", "W"))
     for i in range(4):
-        e2e_step(i)
+        pipe.step(i)
     barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    s_comp.wait_event(ev_out[0]); s_comp.wait_event(ev_out[1])
+    for i in range(args.steps):
+        pipe.step(i)
+    pipe.drain()
     t1.record()
     barrier()
-    ms_e2e = t0.elapsed_time(t1)
-    h = hbuf[0]
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1)) / args.steps
     # the host buffers really hold this step's results: compare with the device-resident path on the same operands
     ref_out = step().detach()
     torch.cuda.synchronize()
-    e2e_ok = bool(torch.allclose(hbuf[(e2e_steps - 1) & 1][0], ref_out.cpu(), rtol=1e-5, atol=1e-6) and
-                  torch.allclose(hbuf[(e2e_steps - 1) & 1][1], x.grad.cpu(), rtol=1e-4, atol=1e-5))
-    if world > 1:
-        tt = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = float(tt.item())
-    ms_e2e /= e2e_steps
-    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ("x", "W", "go", "idx", "cnt", "filt"))
-    d2h = sum(t.numel() * t.element_size() for t in h)
+    last = pipe.hbuf[(args.steps - 1) & 1]
+    e2e_ok = bool(torch.allclose(last[0], ref_out.cpu(), rtol=1e-5, atol=1e-6) and
+                  torch.allclose(last[1], x.grad.cpu(), rtol=1e-4, atol=1e-5))
+
+    model_rec = None
+    if not args.no_extras:
+        try:                                                       # the real data-parallel thing: S3DIS training step, strong scaling
+            model_rec = model_step_bench(S, "s3dis", 8, 8192, world, rank, "strong", max(5, args.steps // 2), 3, dist)
+        except Exception as e:
+            model_rec = {"error": repr(e)}
 
     if rank == 0:
         peak, peak_src = peaks()
         ab_fwd, ab_bwd = algorithmic_bytes(B, N, M, C, r, F, E)
-        # the backward op is several launches (graph transposition, scale, conv_bwd_t_kernel, partial reduce): the roofline
+        # the backward op is several launches (graph transposition, scaled copy, gather kernel, partial reduce): the roofline
         # line charges the op's algorithmic bytes against the time of ALL of them (CUDA events around the op)
         dominant = "conv_bwd_op" if bwd_ms >= fwd_ms else "conv_fwd_kernel"
         ab, tms = (ab_bwd, bwd_ms) if dominant == "conv_bwd_op" else (ab_fwd, fwd_ms)
         ach = ab / (tms * 1e-3) / 1e9
-        # split of the backward op, measured through the planned entry points (same kernels, plan built once)
-        C3 = S.tf_conv3d
-        def _t(fn, n=10):
-            fn(); torch.cuda.synchronize()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(n):
-                fn()
-            b_.record(); torch.cuda.synchronize()
-            return a.elapsed_time(b_) / n
-        split = {}
-        try:
-            plan = C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N)
-            if plan is not None:
-                split["conv_transpose_ms"] = _t(lambda: C3.conv_transpose(d["idx"], d["cnt"], d["filt"], F, N))
-                split["conv_bwd_planned_ms"] = _t(lambda: C3.depthwise_conv3d_grad_planned(d["x"], d["W"], d["go"], d["cnt"], plan, K))
-        except Exception as e:
-            split["planned_error"] = repr(e)
+        sm_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
+        gather_bytes = 4.0 * E * C * r                            # the logical gather both directions perform (E strips of C*r floats)
+        l2_floor_ms = gather_bytes / (L2_CAP_BYTES_PER_CLK * sm_ghz * 1e9) * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "B_per_gpu": B, "N": N, "M": M, "K": K, "Cin": C, "multiplier": r,
-                       "bins": F, "radius": radius, "mean_neighbors": E / (B * M), "parallelism": "dp%d" % world,
-                       "l2": "inputs (%.0f MB/step) larger than L2, no flush" % ((ab_fwd + ab_bwd) / 2e6)},
+            "config": conv_config(args.workload, cfg, F, radius, E, world, "weak"),
             "clocks": clocks,
             "e2e": {"value": world * B * M / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "results_verified": e2e_ok,
-                    "how": "public op on host-fed operands; every step copies 6 inputs H2D and 3 results D2H "
-                           "(pinned memory); steps software-pipelined over 3 streams, double buffered"},
+                    "h2d_bytes_per_step": pipe.h2d, "d2h_bytes_per_step": pipe.d2h, "results_verified": e2e_ok,
+                    "how": "public op on host-fed operands; every step copies features, filter and incoming gradient H2D and "
+                           "3 results D2H (pinned memory, process bound to the GPU's NUMA node: %s); steps software-pipelined "
+                           "over 3 streams, double buffered; graph tensors and their plan resident" % numa},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(dominant), "peak_source": peak_src, "algorithmic_bytes": ab,
-                         "kernel_ms": tms},
+                         "traffic": ncu_traffic(dominant), "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": tms,
+                         "l2_path": {"gather_bytes": gather_bytes, "l2_cap_bytes_per_clk": L2_CAP_BYTES_PER_CLK, "sm_ghz": sm_ghz,
+                                     "floor_ms_if_every_gather_misses_l1": l2_floor_ms,
+                                     "note": "the E*C*r*4-byte gather misses L1 by construction in the transposed backward "
+                                             "(L1 hit 8-15 %, ncu) and moves through L2 at the measured LTS cap; the strict HBM "
+                                             "fraction above cannot exceed algorithmic_bytes / (floor * peak) for this design"}},
             "kernels": {"conv_fwd_ms": fwd_ms, "conv_bwd_ms": bwd_ms,
                         "conv_fwd_gbs": ab_fwd / (fwd_ms * 1e-3) / 1e9, "conv_bwd_gbs": ab_bwd / (bwd_ms * 1e-3) / 1e9,
                         "conv_fwd_frac": ab_fwd / (fwd_ms * 1e-3) / 1e9 / peak, "conv_bwd_frac": ab_bwd / (bwd_ms * 1e-3) / 1e9 / peak,
                         "logical_gather_gbs_fwd": (4.0 * E * C + 4.0 * B * M * C * r + 8.0 * E) / (fwd_ms * 1e-3) / 1e9,
-                        "logical_gather_gbs_bwd": (4.0 * E * C * r + 8.0 * B * N * C + 4.0 * E) / (bwd_ms * 1e-3) / 1e9, **split},
+                        "logical_gather_gbs_bwd": (4.0 * E * C * r + 8.0 * B * N * C + 4.0 * E) / (bwd_ms * 1e-3) / 1e9},
+            "planned": planned,
         }
+        if model_rec is not None:
+            line["model"] = model_rec
         if world == 1 and not args.no_extras:
             try:
                 line["cpu_baseline"] = cpu_baseline(host, cfg)

@@ -25,51 +25,12 @@ s3g_util = S.sph3gcn_util
 M = S.models
 
 
-def make_config(model, N, K=None):
-    if model == "modelnet":
-        return M.configs.modelnet(N)
-    if model == "shapenet":
-        return M.configs.shapenet(N, nn_uplimit=K or 32)       # BASELINE.json configs[2]: K = 32
-    return M.configs.s3dis(N)
-
-
-DEFAULT_SHAPE = {"modelnet": (32, 10000), "shapenet": (16, 2048), "s3dis": (8, 8192)}
+train_step = S.utils.train_step
+make_config, DEFAULT_SHAPE = train_step.make_config, train_step.DEFAULT_SHAPE
 
 
 def make_step(B, N, seed=7, model="modelnet", K=None):
-    """-> (step function, config).  step() = clear collections, forward, the reference's loss, backward."""
-    dev = torch.device("cuda", torch.cuda.current_device())
-    g = torch.Generator().manual_seed(seed)
-    cfg = make_config(model, N, K)
-    s3g_util.reset_variables()
-    xyz = torch.rand(B, N, 3, generator=g)                    # unit cube, like a normalised cloud / a 1 m S3DIS block
-    if model == "modelnet":
-        pts, label = xyz.to(dev), torch.randint(0, cfg.num_cls, (B,), generator=g).to(dev)
-    elif model == "shapenet":                                 # xyz + normals, 50 part classes (shapenet_seg/train_shapenet.py)
-        pts = torch.cat([xyz, torch.rand(B, N, 3, generator=g)], dim=2).to(dev)
-        label = torch.randint(0, 50, (B, N), generator=g).to(dev)
-    else:                                                     # xyz + rgb (INPUT_DIM = 6, s3dis_seg/train_s3dis.py:57)
-        pts = torch.cat([xyz, torch.rand(B, N, 3, generator=g)], dim=2).to(dev)
-        label = torch.randint(0, cfg.num_cls, (B, N), generator=g).to(dev)
-        inner = (torch.rand(B, N, generator=g) < 0.7).to(torch.int32).to(dev)
-
-    def step():
-        s3g_util.clear_collections()
-        for p in s3g_util.trainable_variables():
-            p.grad = None
-        if model == "modelnet":
-            pred, end = M.SPH3D_modelnet.get_model(pts, True, cfg)
-            M.SPH3D_modelnet.get_loss(pred, label, end)
-        elif model == "shapenet":
-            pred, end = M.SPH3D_shapenet.get_model(pts, 50, True, cfg)
-            M.SPH3D_shapenet.get_loss(pred, label, end)
-        else:
-            pred, end = M.SPH3D_s3dis.get_model(pts, True, cfg)
-            M.SPH3D_s3dis.get_loss(pred, label, end, inner)
-        loss = sum(s3g_util.get_collection('losses'))         # tf.add_n(tf.get_collection('losses')) in the train scripts
-        loss.backward()
-        return pred, end, loss
-
+    step, cfg, _ = train_step.make_step(B, N, seed, model, K)
     return step, cfg
 
 

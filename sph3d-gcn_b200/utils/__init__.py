@@ -1,1 +1,1 @@
-from . import data_util, dist_util, graph_step   # noqa: F401
+from . import data_util, dist_util, graph_step, train_step   # noqa: F401

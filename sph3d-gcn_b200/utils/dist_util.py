@@ -51,3 +51,102 @@ def allreduce_gradients(tensors, group=None, average=False):
         t.copy_(flat[off:off + n].view_as(t))
         off += n
     return flat.numel() * flat.element_size()
+
+
+class GradBuckets(object):
+    """Persistent flat gradient storage + bucketed, overlapped all-reduce.
+
+    Every parameter's .grad is a VIEW into one flat fp32 buffer (no torch.cat round trip before the collective, no copy
+    back after it).  Parameters are grouped into `n_buckets` contiguous buckets in REVERSE registration order -- the order
+    in which a backward pass finishes them -- and a post-accumulate-grad hook starts a bucket's all-reduce on a side
+    stream the moment its last gradient is written, so the collective of the decoder's gradients runs under the backward
+    of the encoder.  finish() joins the side stream (and applies the 1/world average).  The hooks, the side stream and
+    the NCCL calls are all stream-ordered, so a step that uses this can be captured in a CUDA graph as a whole.
+
+        buckets = GradBuckets(params, n_buckets=4)     # after the variables exist
+        buckets.zero(); loss.backward(); buckets.finish()
+    With torch.distributed uninitialised (or world size 1) zero()/finish() still work and nothing is reduced.
+    """
+
+    def __init__(self, params, n_buckets=4, group=None, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.average = group, average
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        order = list(reversed(self.params))                      # backward finishes the last layers first
+        n_buckets = max(1, min(int(n_buckets), len(order)))
+        target = (total + n_buckets - 1) // n_buckets
+        self.bounds, self.bucket_of, self.pending0 = [], {}, []
+        off, start, count = 0, 0, 0
+        for p in order:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.bucket_of[id(p)] = len(self.bounds)
+            off += p.numel()
+            count += 1
+            if off - start >= target or p is order[-1]:
+                self.bounds.append((start, off))
+                self.pending0.append(count)
+                start, count = off, 0
+        self.pending = list(self.pending0)
+        self.cuda = dev.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.cuda else None
+        self.works = []
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.bytes_reduced = 0
+
+    def zero(self):
+        """reset the gradient storage in place (the views stay attached) and re-arm the buckets"""
+        self.flat.zero_()
+        if any(p.grad is None for p in self.params):            # a caller set .grad = None in between: re-attach the views
+            self.reattach()
+        self.pending = list(self.pending0)
+        self.works = []
+        self.bytes_reduced = 0
+
+    def reattach(self):
+        off = 0
+        for p in reversed(self.params):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def _launch(self, b):
+        if self.world == 1:
+            return
+        lo, hi = self.bounds[b]
+        chunk = self.flat[lo:hi]
+        self.bytes_reduced += chunk.numel() * 4
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _hook(self, p):
+        b = self.bucket_of[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def finish(self):
+        """every bucket reduced (buckets whose hooks never fired -- unused parameters -- are reduced here) and averaged;
+        returns the bytes that crossed the collective"""
+        for b, left in enumerate(self.pending):
+            if left > 0:
+                self.pending[b] = 0
+                self._launch(b)
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+        if self.average and self.world > 1:
+            self.flat.mul_(1.0 / self.world)
+        return self.bytes_reduced
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []

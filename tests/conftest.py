@@ -28,9 +28,17 @@ def pkg():
 
 @pytest.fixture(scope="session")
 def ref():
-    """The unmodified reference kernels (oracle/_ref), or None when the .so did not travel."""
+    """The unmodified reference kernels (oracle/_ref).  On a GPU box their absence is an ERROR, not a skip: every
+    reference comparison of the -m gpu suite would silently vanish (oracle/_ref is built by oracle/Makefile here, where
+    /root/reference exists, and travels with the snapshot).  Without a GPU (no -m gpu test runs) it is None."""
     import ref_gpu
-    return ref_gpu if ref_gpu.available() else None
+    import torch
+    if ref_gpu.available():
+        return ref_gpu
+    if torch.cuda.is_available():
+        pytest.fail("oracle/_ref/libsph3d_ref.so is missing on a GPU box: run `make -C oracle ref` where /root/reference "
+                    "exists (python -c 'import __graft_entry__ as g; g.build()') before shipping the snapshot")
+    return None
 
 
 @pytest.fixture()

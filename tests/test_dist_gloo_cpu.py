@@ -72,3 +72,72 @@ def test_gradient_allreduce_world2(tmp_path):
     scale = np.abs(full).max()
     assert np.abs(red - full).max() <= 1e-5 * scale
     assert (np.load(tmp_path / "bias.npy") == 3.0).all()
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sph3d_gcn_b200  # noqa: F401
+    from importlib import import_module
+    du = import_module("sph3d_gcn_b200.utils.dist_util")
+    torch.manual_seed(0)                                          # same weights on every rank
+    layers = [torch.nn.Linear(8, 16), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4)]
+    unused = torch.nn.Parameter(torch.ones(3))                    # never reached by backward: reduced by finish()
+    params = [p for l in layers for p in l.parameters()] + [unused]
+    buckets = du.GradBuckets(params, n_buckets=3, average=True)
+    assert 2 <= len(buckets.bounds) <= 3 and buckets.flat.numel() == sum(p.numel() for p in params)
+    g = torch.Generator().manual_seed(100)
+    xs = torch.randn(world, 5, 8, generator=g)                    # the global batch; this rank owns slice `rank`
+    for it in range(2):                                           # second iteration: zero() re-arms buckets and views
+        buckets.zero()
+        h = xs[rank]
+        for l in layers:
+            h = torch.tanh(l(h))
+        h.sum().backward()
+        nbytes = buckets.finish()
+        assert nbytes == buckets.flat.numel() * 4
+        assert all(p.grad.data_ptr() >= buckets.flat.data_ptr() for p in params)     # still views of the flat buffer
+    if rank == 0:
+        torch.save([p.grad.clone() for p in params], os.path.join(out_dir, "bucket_grads.pt"))
+        torch.save((xs, [p.detach().clone() for p in params]), os.path.join(out_dir, "bucket_inputs.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_grad_buckets_world2(tmp_path):
+    """flat gradient storage with views + hook-driven bucketed all-reduce == mean over ranks of the per-rank gradients"""
+    world, port = 2, _free_port()
+    mp.spawn(_bucket_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(tmp_path / "bucket_grads.pt")
+    xs, weights = torch.load(tmp_path / "bucket_inputs.pt")
+    ws = [w.clone().requires_grad_(True) for w in weights]
+    total = 0
+    for r in range(world):
+        h = xs[r]
+        for i in range(3):
+            h = torch.tanh(h @ ws[2 * i].t() + ws[2 * i + 1])
+        total = total + h.sum()
+    (total / world).backward()
+    for g, w in zip(got[:-1], ws[:-1]):
+        assert torch.allclose(g, w.grad, rtol=1e-5, atol=1e-6)
+    assert (got[-1] == 0).all()
+
+
+def test_grad_buckets_single_process():
+    sys.path.insert(0, ROOT)
+    from importlib import import_module
+    du = import_module("sph3d_gcn_b200.utils.dist_util")
+    lin = torch.nn.Linear(4, 3)
+    b = du.GradBuckets(list(lin.parameters()), n_buckets=8)
+    b.zero()
+    lin(torch.ones(2, 4)).sum().backward()
+    assert b.finish() == 0 and torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
+    lin.weight.grad = None
+    b.zero()                                                       # re-attaches the views
+    lin(torch.ones(2, 4)).sum().backward()
+    assert lin.weight.grad.data_ptr() >= b.flat.data_ptr() and torch.allclose(lin.weight.grad, torch.full((3, 4), 2.0))
+    b.close()

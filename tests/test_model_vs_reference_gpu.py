@@ -14,48 +14,6 @@ from common import assert_close
 pytestmark = pytest.mark.gpu
 
 
-def _reference_ops(ref):
-    """torch.autograd wrappers around the reference launchers (gradients = the reference's own *Grad launchers)"""
-
-    class Conv(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, input, filter, nn_index, nn_count, bin_index):
-            ctx.save_for_backward(input, filter, nn_index, nn_count, bin_index)
-            return ref.depthwise_conv3d(input.contiguous(), filter.contiguous(), nn_index, nn_count, bin_index)
-
-        @staticmethod
-        def backward(ctx, g):
-            input, filter, nn_index, nn_count, bin_index = ctx.saved_tensors
-            gi, gf = ref.depthwise_conv3d_grad(input.contiguous(), filter.contiguous(), g.contiguous(), nn_index, nn_count, bin_index)
-            return gi, gf, None, None, None
-
-    class MaxPool(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, input, nn_index, nn_count):
-            out, max_index = ref.max_pool3d(input.contiguous(), nn_index, nn_count)
-            ctx.save_for_backward(input, max_index)
-            ctx.mark_non_differentiable(max_index)
-            return out, max_index
-
-        @staticmethod
-        def backward(ctx, g, _):
-            input, max_index = ctx.saved_tensors
-            return ref.max_pool3d_grad(input.contiguous(), g.contiguous(), max_index), None, None
-
-    class MeanUnpool(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, input, nn_index, nn_count):
-            ctx.save_for_backward(input, nn_index, nn_count)
-            return ref.mean_interpolate(input.contiguous(), nn_index, nn_count)
-
-        @staticmethod
-        def backward(ctx, g):
-            input, nn_index, nn_count = ctx.saved_tensors
-            return ref.mean_interpolate_grad(input.contiguous(), g.contiguous(), nn_index, nn_count), None, None
-
-    return Conv, MaxPool, MeanUnpool
-
-
 def _run(pkg, model, pts, label, inner, cfg):
     u, M = pkg.sph3gcn_util, pkg.models
     u.clear_collections()
@@ -77,8 +35,7 @@ def _run(pkg, model, pts, label, inner, cfg):
 
 @pytest.mark.parametrize("model", ["s3dis", "modelnet"])
 def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, monkeypatch, model):
-    if ref is None:
-        pytest.skip("oracle/_ref/libsph3d_ref.so not built")
+    assert ref is not None                                  # conftest fails the run when oracle/_ref did not travel
     u, M = pkg.sph3gcn_util, pkg.models
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(77)
@@ -101,16 +58,8 @@ def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, m
             t.copy_(torch.rand(t.shape, generator=g).to(dev) * 0.5 + (0.75 if k.endswith("variance") else -0.25))
     pred_a, loss_a, names, grads_a = _run(pkg, model, pts, label, inner, cfg)
 
-    Conv, MaxPool, MeanUnpool = _reference_ops(ref)
-    monkeypatch.setattr(u, "neighbor_fn", ref.build_sphere_neighbor)
-    monkeypatch.setattr(u, "spherical_kernel", ref.spherical_kernel)
-    monkeypatch.setattr(u, "farthest_point_sample", ref.farthest_point_sample)
-    monkeypatch.setattr(u.tf_conv3d, "depthwise_conv3d", lambda i, f, a, b, c: Conv.apply(i, f, a, b, c))
-    monkeypatch.setattr(u.tf_pool3d, "max_pool3d", lambda i, a, b: MaxPool.apply(i, a, b))
-    monkeypatch.setattr(u.tf_unpool3d, "mean_interpolate", lambda i, a, b: MeanUnpool.apply(i, a, b))
-    monkeypatch.setattr(u, "FUSED_TAIL", False)
-    monkeypatch.setattr(u, "SPLIT_K_WEIGHT_GRAD", False)
-    monkeypatch.setattr(u, "TENSOR_CORE_DENSE", False)
+    import ref_model
+    ref_model.install(pkg, monkeypatch.setattr)           # every custom op -> the unmodified reference kernel, fused paths off
     pred_b, loss_b, _, grads_b = _run(pkg, model, pts, label, inner, cfg)
 
     assert_close(pred_a, pred_b, 1e-3, "%s logits: this library vs reference kernels" % model)

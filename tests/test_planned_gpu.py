@@ -68,9 +68,11 @@ def test_spherical_kernel_emits_the_plans(pkg, oracle, monkeypatch):
     L = pkg._lib.lib()
     out = pkg.tf_conv3d.depthwise_conv3d(xt, Wt, ti, tc, tfilt)
     assert L.sph3d_last_launch_count() == 1                                   # the gather kernel alone
-    out.backward(T(go))
+    out.backward(T(go))                                                       # (autograd thread: its launch counter is its own)
+    assert len(tfilt._sph3d_plans) == 2                                       # nothing was rebuilt
+    bplan = [v for k, v in tfilt._sph3d_plans.items() if k[0] == "bwd"][0]
+    pkg.tf_conv3d.depthwise_conv3d_grad_planned(T(x), T(W), T(go), tc, bplan, K)
     assert L.sph3d_last_launch_count() == 3                                   # scaled copy + gather pass + partial reduction
-    assert len(tfilt._sph3d_plans) == 2
     assert_close(A(out), oracle.depthwise_conv3d(x, W, idx, cnt, filt, 1), 1e-5)
     gi, gf = oracle.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
     assert_close(A(xt.grad), gi, 1e-5); assert_close(A(Wt.grad), gf, 1e-5)
