@@ -16,9 +16,9 @@ def _network(points, num_cls, is_training, config):
                  is_training=is_training)
     stem = s3g_util.pointwise_conv3d(points, config.mlp, 'mlp1', **layer)
     net = _stages.segmentation_trunk(xyz, stem, config, is_training)
-    end_points['feats'] = net
     net = s3g_util.pointwise_conv3d(net, config.mlp, 'mlp2', **layer)
     net = torch.cat((net, stem), dim=2)
+    end_points['feats'] = net                       # after the skip concat, as SPH3D_shapenet.py:108-111
     net = s3g_util.pointwise_conv3d(net, num_cls, scope='logits', with_bn=False, with_bias=config.with_bias,
                                     activation_fn=None, is_training=is_training)
     return net, end_points

@@ -50,11 +50,13 @@ def build_sphere_neighbor(database, query, radius=0.1, dilation_rate=None, nnsam
 
 @torch.no_grad()
 def build_cube_neighbor(database, query, length=0.1, dilation_rate=None, nnsample=100, gridsize=3):
-    '''
-    Output:
-        nn_index: (batch, mpoint, nnsample, 2) int32 array, neighbor and filter bin indices
-        nn_count: (batch, mpoint) int32 array, number of neighbors
-    '''
+    """Axis-aligned cube query with a gridsize^3 bin per hit (tf_nnquery_gpu.cu:72-113).
+
+    Per query point: the first `nnsample` database points (ascending id) whose offset lies inside the cube of edge
+    `length` (times `dilation_rate`), each with the cell of the gridsize x gridsize x gridsize subdivision it falls in.
+    Returns nn_index (B, M, nnsample, 2) int32 = (point id, x*g*g + y*g + z) pairs and nn_count (B, M) int32, which may
+    be 0 (no radius growth here).  No model of the reference uses it; kept for API completeness.
+    """
     database = _xyz(database, "database")
     query = _xyz(query, "query")
     if dilation_rate is not None:

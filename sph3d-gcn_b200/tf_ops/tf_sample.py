@@ -7,13 +7,11 @@ from .tf_nnquery import _xyz
 
 @torch.no_grad()
 def farthest_point_sample(neursize, database):
-    '''
-    input:
-        neursize: int32, the number of neurons/points to be sampled
-        database: (batch, npoint, 3) float32 array, database points
-    returns:
-        neuron_index: (batch_size, neursize) int32 array, index of sampled neurons in the database
-    '''
+    """Farthest point sampling: `neursize` point ids per cloud, (B, neursize) int32.
+
+    Starts from point 0 of each cloud of `database` (B, N, 3+) and repeatedly takes the point whose squared distance to
+    the set picked so far is largest, with the reference kernel's tie rule -- bit-identical picks.
+    """
     database = _xyz(database, "database")
     neursize = int(neursize)
     if not neursize > 0:

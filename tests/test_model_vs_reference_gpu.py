@@ -22,6 +22,9 @@ def _run(pkg, model, pts, label, inner, cfg):
     if model == "s3dis":
         pred, end = M.SPH3D_s3dis.get_model(pts, True, cfg)
         loss = M.SPH3D_s3dis.get_loss(pred, label, end, inner)
+    elif model == "shapenet":
+        pred, end = M.SPH3D_shapenet.get_model(pts, 50, True, cfg)
+        loss = M.SPH3D_shapenet.get_loss(pred, label, end)
     else:
         pred, end = M.SPH3D_modelnet.get_model(pts, False, cfg)          # inference mode: no dropout, moving statistics
         loss = M.SPH3D_modelnet.get_loss(pred, label, end)
@@ -33,7 +36,7 @@ def _run(pkg, model, pts, label, inner, cfg):
     return pred.detach().cpu().numpy().copy(), float(loss.detach()), names, grads
 
 
-@pytest.mark.parametrize("model", ["s3dis", "modelnet"])
+@pytest.mark.parametrize("model", ["s3dis", "modelnet", "shapenet"])
 def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, monkeypatch, model):
     assert ref is not None                                  # conftest fails the run when oracle/_ref did not travel
     u, M = pkg.sph3gcn_util, pkg.models
@@ -45,6 +48,12 @@ def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, m
         pts = torch.rand(B, N, 6, generator=g).to(dev)
         label = torch.randint(0, 13, (B, N), generator=g).to(dev)
         inner = (torch.rand(B, N, generator=g) < 0.6).int().to(dev)
+    elif model == "shapenet":                             # BASELINE.json configs[2]: K = 32, full 2048-point clouds
+        B, N = 2, 2048
+        cfg = M.configs.shapenet(N, nn_uplimit=32)
+        pts = torch.rand(B, N, 6, generator=g).to(dev)
+        label = torch.randint(0, 50, (B, N), generator=g).to(dev)
+        inner = None
     else:
         B, N = 2, 2048
         cfg = M.configs.modelnet(N)
@@ -76,4 +85,4 @@ def test_network_on_this_library_equals_network_on_reference_kernels(pkg, ref, m
         tol = 2e-2 * float(np.abs(b).max()) + floor
         assert err.max() <= tol, "%s grad of %s: max err %.3e > %.3e (scale %.3e)" % (model, name, err.max(), tol, np.abs(b).max())
         checked += 1
-    assert checked >= (60 if model == "s3dis" else 30)
+    assert checked >= {"s3dis": 60, "shapenet": 60, "modelnet": 30}[model]
