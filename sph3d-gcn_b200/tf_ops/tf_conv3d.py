@@ -196,12 +196,13 @@ def emit_plans(nn_index, nn_count, bin_index, num_bins, npoint, backward=True):
         _shared_plan("bwd", nn_index, nn_count, bin_index, num_bins, npoint)
 
 
-def _use_planned(C, r):
+def _use_planned(C, r, rows):
     """whether a shared plan pays for this layer.  r = 1: always (the one-call form transposes anyway).  r = 2: the
-    transposed form gathers C*r floats per edge where the row-owned one gathers C and reduces C; with the plan shared by
-    the level's two convolutions it measured faster at every S3DIS / Cfg-T shape (profiles/r2_stage_a.json: 2.03 vs
-    2.59 ms at C = 128, 0.25 vs 0.39 ms at C = 64), so it is used whenever the plan applies."""
-    return r in (1, 2)
+    transposed form gathers C*r floats per edge where the row-owned one gathers C and reduces C; measured over every layer
+    of the S3DIS network (profiles/r2_s3dis_layers.json, plan shared by the level's two convolutions) it wins up to
+    C*r = 512 on levels of >= 4096 rows (0.24 vs 0.39 ms at C = 64, 0.22 vs 0.32 ms at C = 256) and loses beyond
+    (C = 512: 0.76 vs 0.60 ms) and on the deep, tiny levels, where the plan build is not paid back."""
+    return r == 1 or (r == 2 and C * r <= 512 and rows >= 4096)
 
 
 class _DepthwiseConv3d(torch.autograd.Function):
@@ -216,7 +217,7 @@ class _DepthwiseConv3d(torch.autograd.Function):
         input, filter, nn_index, nn_count, bin_index = ctx.saved_tensors
         grad_output = grad_output.contiguous()
         F, C, r = filter.shape
-        if SHARE_PLANS and _use_planned(C, r):
+        if SHARE_PLANS and _use_planned(C, r, input.shape[0] * ctx.graph[0].shape[1]):
             g_idx, g_cnt, g_bin = ctx.graph
             L = _lib.lib()
             B, N = input.shape[0], input.shape[1]

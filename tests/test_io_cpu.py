@@ -275,3 +275,48 @@ def test_shapenet_and_modelnet_records(pkg, tfr, tmp_path):
         for x, l in zip(xs, ls):
             if sum(1 for _, l2 in clouds if l2 == int(l)) == 1:
                 assert np.array_equal(x, by_label[int(l)])
+
+
+def test_scene_merge_restates_the_matlab_script(pkg):
+    """post-merging/s3dis_merge.m:37-81 written out literally (loops, 1-based -> 0-based) vs io/s3dis_merge.py"""
+    mg = pkg.io.s3dis_merge
+    rng = np.random.default_rng(5)
+    P, C = 400, 13
+    voxel_xyz = rng.random((P, 3))
+    gt = rng.integers(0, C, P)
+    blocks = []
+    for k in range(5):                                           # overlapping blocks: random subsets of the scene
+        n = int(rng.integers(120, 260))
+        index = rng.choice(P, n, replace=False)
+        inner = (rng.random(n) < 0.6).astype(np.int32)
+        logits = (rng.standard_normal((n, C)) * rng.integers(1, 4)).astype(np.float32)     # summed over 1-3 draws
+        blocks.append((logits, inner, index))
+    # literal restatement
+    want = np.zeros((P, C))
+    for logits, inner, index in blocks:
+        for row in range(len(index)):
+            if inner[row] != 1:
+                continue
+            v = logits[row].astype(np.float64)
+            v = v / np.sqrt(np.sum(v ** 2))
+            v = np.exp(v) / np.sum(np.exp(v))
+            want[index[row]] += v
+    pred, label = mg.merge_scene(P, blocks, C)
+    assert np.allclose(pred, want, rtol=1e-12, atol=0)
+    assert (label == want.argmax(1)).all()
+    assert np.allclose(mg.block_confidence(blocks[0][0]).sum(1), 1.0)
+    assert (mg.block_confidence(np.zeros((2, C))) == 0).all()     # never-drawn rows contribute nothing (MATLAB: NaN)
+    with pytest.raises(ValueError):
+        mg.merge_scene(10, blocks, C)
+    # nearest-voxel propagation to the full cloud + IoU totals
+    full_xyz = voxel_xyz[rng.integers(0, P, 1500)] + rng.normal(0, 1e-4, (1500, 3))
+    d = ((full_xyz[:, None, :] - voxel_xyz[None]) ** 2).sum(-1)
+    assert (mg.propagate_to_full_cloud(voxel_xyz, label, full_xyz) == label[d.argmin(1)]).all()
+    full_gt = gt[d.argmin(1)]
+    full_pred = label[d.argmin(1)]
+    m = mg.SceneIoU(C)
+    m.update(full_pred[:700], full_gt[:700]); m.update(full_pred[700:], full_gt[700:])
+    res = m.result()
+    for c in range(C):
+        inter, uni = ((full_pred == c) & (full_gt == c)).sum(), ((full_pred == c) | (full_gt == c)).sum()
+        assert m.intersect[c] == inter and m.union[c] == uni and (uni == 0 or abs(res["iou"][c] - inter / uni) < 1e-12)
