@@ -22,8 +22,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="modelnet")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--B", type=int, default=0, help="clouds per step (default: the config's batch); B=1 = one rank's share of S3DIS at 8 GPUs")
     a = ap.parse_args()
     B, N = be.DEFAULT_SHAPE[a.model]
+    B = a.B or B
     step, cfg = be.make_step(B, N, model=a.model)
     run_step = be.S.utils.graph_step.GraphedStep(step, be.s3g_util.trainable_variables, warmup=3) if a.graph else step
     for _ in range(3):
@@ -71,7 +73,8 @@ def main():
            "top_gaps": [{"us": g[0], "after": (g[1] or "")[:80], "before": g[2][:80]} for g in gaps[:25]],
            "top_kernels": sorted(([n, c, round(t, 1)] for n, (c, t) in by_name.items()), key=lambda r: -r[2])[:25]}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    fn = os.path.join(ROOT, "gpurun_out", "timeline_%s%s.json" % (a.model, "_graph" if a.graph else ""))
+    out["B"] = B
+    fn = os.path.join(ROOT, "gpurun_out", "timeline_%s%s%s.json" % (a.model, "_graph" if a.graph else "", "_B%d" % B if a.B else ""))
     json.dump(out, open(fn, "w"), indent=1)
     print(json.dumps({k: out[k] for k in ("model", "graph", "kernels_in_step", "span_us", "busy_union_us", "idle_us", "sum_kernel_us",
                                           "gap_histogram_us", "idle_in_gaps_ge_10us")}))

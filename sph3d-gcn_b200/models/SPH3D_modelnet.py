@@ -26,6 +26,7 @@ def _network(points, is_training, config):
                  is_training=is_training)
     net = s3g_util.pointwise_conv3d(xyz, config.mlp, 'mlp1', **layer)
     summary = []
+    s3g_util.prefetch_samples(xyz, config.num_sample, config.sample)      # the whole FPS chain starts now, on the side stream
     for level in range(len(config.radius)):
         if config.use_raw:
             net = torch.cat([net, xyz], dim=-1)

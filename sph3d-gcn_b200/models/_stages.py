@@ -54,6 +54,7 @@ def decoder(net, xyz_pyramid, skips, config, is_training):
 def segmentation_trunk(xyz, net, config, is_training):
     """encoder + decoder; returns per-point features at the input resolution"""
     pyramid, skips = [xyz], []
+    s3g_util.prefetch_samples(xyz, config.num_sample, config.sample)      # the whole FPS chain starts now, on the side stream
     for level in range(len(config.radius)):
         feats, coarse, net = encoder_level(xyz, net, level, config, is_training)
         skips.append(feats)

@@ -221,6 +221,7 @@ else:
 
     def join_pending_samples():
         """make the current stream wait for every sampler still running on the side stream"""
+        _PREFETCHED.clear()
         while _PENDING_SAMPLES:
             event, indices = _PENDING_SAMPLES.pop()
             cur = torch.cuda.current_stream(indices.device)
@@ -241,6 +242,42 @@ else:
                     break
 
 
+    # Sampling pyramid ahead of the network.  FPS of level l+1 needs only the xyz picked at level l -- no features -- so the
+    # whole chain (8192 -> 2048 -> 768 -> 384 -> 128 in SPH3D_s3dis: 3 328 sequential rounds, 1.5 ms on one SM per cloud) can
+    # run on the side stream from the first instant instead of level by level behind the convolutions.  prefetch_samples
+    # enqueues it; build_graph(xyz_l, ..., sample_method='FPS') then finds the picks of ITS xyz tensor instead of launching
+    # FPS, and gather_nd(xyz_l, indices_l) returns the coarse cloud the chain already gathered (same values bit for bit).
+    _PREFETCHED = {}               # id(xyz tensor) -> (xyz tensor, num_sample, indices)
+
+
+    def prefetch_samples(xyz, num_samples, sample_method='FPS'):
+        """start FPS for every level of the pyramid rooted at `xyz` on the side stream; no-op for other samplers / CPU"""
+        _PREFETCHED.clear()
+        if sample_method != 'FPS' or not xyz.is_cuda or not _ASYNC_SAMPLING[0]:
+            return
+        cur = torch.cuda.current_stream(xyz.device)
+        side = _side_stream(xyz.device)
+        side.wait_stream(cur)
+        batch_size = xyz.shape[0]
+        level_xyz = xyz
+        with torch.cuda.stream(side):
+            for num_sample in num_samples:
+                if num_sample is None or num_sample <= 1 or num_sample > level_xyz.shape[1]:
+                    break
+                sample_index = farthest_point_sample(num_sample, level_xyz)
+                indices = _sample_indices(sample_index, batch_size, num_sample)
+                coarse = level_xyz[indices[..., 0].long(), indices[..., 1].long()].contiguous()
+                event = torch.cuda.Event()
+                event.record(side)
+                indices._sph3d_ready = event
+                indices._sph3d_src = level_xyz
+                indices._sph3d_coarse = coarse
+                _PENDING_SAMPLES.append((event, indices))
+                _PREFETCHED[id(level_xyz)] = (level_xyz, int(num_sample), indices)
+                level_xyz = coarse
+        xyz.record_stream(side)
+
+
     def _sample_indices(sample_index, batch_size, num_sample):
         batch_indices = torch.arange(batch_size, device=sample_index.device, dtype=sample_index.dtype)
         batch_indices = batch_indices.view(-1, 1, 1).expand(-1, int(num_sample), 1)
@@ -254,6 +291,10 @@ else:
         # critical path.
         fps_event = None
         batch_size = xyz.shape[0]
+        ahead = _PREFETCHED.get(id(xyz)) if (num_sample is not None and sample_method == 'FPS') else None
+        if ahead is not None and ahead[0] is xyz and ahead[1] == int(num_sample):
+            intra_idx, intra_cnt, intra_dst = neighbor_fn(xyz, xyz, radius=radius, nnsample=nn_uplimit)
+            return intra_idx, intra_cnt, intra_dst, ahead[2]            # picks already on their way (prefetch_samples)
         if num_sample is not None and sample_method == 'FPS' and xyz.is_cuda:
             cur = torch.cuda.current_stream(xyz.device)
             side = _side_stream(xyz.device)
@@ -303,6 +344,10 @@ else:
         the row selection the models apply to xyz / intra_idx / intra_cnt / intra_dst
         (models/SPH3D_s3dis.py:68-72)."""
         _join_sample(indices)
+        if getattr(indices, "_sph3d_src", None) is params:                # the prefetched chain gathered this cloud already
+            coarse = indices._sph3d_coarse
+            coarse.record_stream(torch.cuda.current_stream(coarse.device))
+            return coarse
         b = indices[..., 0].long()
         s = indices[..., 1].long()
         return params[b, s].contiguous()

@@ -167,3 +167,40 @@ def test_async_sampling_joins_before_indices_are_read(pkg, oracle):
     _, _, _, indices = u.build_graph(xyz, 0.05, 16, S, sample_method='FPS')      # outside the block: joined on return
     assert getattr(indices, "_sph3d_ready", None) is None
     assert_equal(indices[..., 1].cpu().numpy(), want, "FPS ids, synchronous")
+
+
+def test_sampling_pyramid_prefetch_changes_nothing_but_the_schedule(pkg, monkeypatch):
+    """prefetch_samples runs the whole FPS chain ahead on the side stream; build_graph / gather_nd then hand out ITS picks
+    and coarse clouds.  Forward results must be bit-identical to the level-by-level schedule."""
+    u, M = pkg.sph3gcn_util, pkg.models
+    B, N = 2, 2048
+    cfg = M.configs.s3dis(N)
+    g = torch.Generator().manual_seed(5)
+    pts = torch.rand(B, N, 6, generator=g).to("cuda:0")
+    u.reset_variables()
+    with torch.no_grad():
+        u.clear_collections()
+        a, _ = M.SPH3D_s3dis.get_model(pts, False, cfg)
+        torch.cuda.synchronize()
+        assert not u._PREFETCHED and not u._PENDING_SAMPLES                # everything joined and released
+        seen = []
+        real = u.prefetch_samples
+        monkeypatch.setattr(u, "prefetch_samples", lambda *args, **kw: seen.append(args[1]))
+        u.clear_collections()
+        b, _ = M.SPH3D_s3dis.get_model(pts, False, cfg)
+        torch.cuda.synchronize()
+    assert seen == [cfg.num_sample]
+    assert torch.equal(a, b)
+    # the chain itself: picks per level equal FPS run level by level
+    monkeypatch.setattr(u, "prefetch_samples", real)
+    xyz = pts[:, :, :3].contiguous()
+    with u.async_sampling():
+        u.prefetch_samples(xyz, cfg.num_sample, 'FPS')
+        level = xyz
+        for s in cfg.num_sample:
+            _, _, _, ind = u.build_graph(level, 0.2, 16, s, sample_method='FPS')
+            want = pkg.tf_sample.farthest_point_sample(s, level)
+            coarse = u.gather_nd(level, ind)
+            assert torch.equal(ind[..., 1], want)
+            assert torch.equal(coarse, level[torch.arange(B, device=level.device)[:, None], want.long()])
+            level = coarse
