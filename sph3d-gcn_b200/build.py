@@ -47,8 +47,16 @@ def _extra_flags(source):
     if not source.startswith("dense_"):
         return []
     root = cutlass_root()
-    if root is None:                                   # entry points still exist and return cudaErrorNotSupported
-        return ["-DSPH3D_NO_CUTLASS"]
+    if root is None:
+        # No silent downgrade: without the header tree the tcgen05 pointwise products cannot be built and the layer
+        # library would quietly fall back to the library GEMM.  Point SPH3D_CUTLASS_ROOT at a CUTLASS >= 4.x checkout
+        # (the directory that holds include/ and tools/util/include), or opt out explicitly with SPH3D_NO_CUTLASS=1:
+        # the dense entry points then exist and return cudaErrorNotSupported (801).
+        if os.environ.get("SPH3D_NO_CUTLASS") == "1":
+            return ["-DSPH3D_NO_CUTLASS"]
+        raise RuntimeError("sph3d-gcn_b200: CuTe/CUTLASS headers not found (looked at $SPH3D_CUTLASS_ROOT and the trees "
+                           "vendored in the flashinfer / tilelang packages). Set SPH3D_CUTLASS_ROOT, or SPH3D_NO_CUTLASS=1 "
+                           "to build without the tcgen05 pointwise products.")
     return ["-I", os.path.join(root, "include"), "-I", os.path.join(root, "tools", "util", "include"),
             "--expt-relaxed-constexpr", "-w"]
 

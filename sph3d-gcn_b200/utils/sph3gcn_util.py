@@ -51,7 +51,9 @@ else:
             self.params = OrderedDict()       # name -> torch.nn.Parameter
             self.buffers = OrderedDict()      # name -> tensor (BN moving statistics)
             self.collections = {"losses": [], "regularization_losses": []}
-            self.pending_l2 = {"losses": [], "regularization_losses": []}   # (variable, scale) L2 terms, see get_collection
+            # L2 terms (weight decay, BN regularisers) per collection, keyed by the variable's identity: a variable registers
+            # its term once however often the layer runs (TensorFlow adds the regulariser when the variable is created)
+            self.pending_l2 = {"losses": {}, "regularization_losses": {}}
             self.scope = []
 
         def full_name(self, name):
@@ -111,18 +113,18 @@ else:
         """tf.get_collection.  The per-variable L2 terms (weight decay, BN regularizers) registered since the last
         clear_collections() are materialised here as ONE fused term: only their sum is ever consumed
         (tf.add_n(tf.get_collection('losses')) in the reference's train scripts)."""
-        pending = _STORE.pending_l2.get(name)
-        if pending:
-            _STORE.collections[name].append(_L2Sum.apply(tuple(sc for _, sc in pending), *[v for v, _ in pending]))
-            del pending[:]
-        return list(_STORE.collections.get(name, []))
+        items = list(_STORE.collections.get(name, []))
+        pending = list((_STORE.pending_l2.get(name) or {}).values())
+        if pending:                     # built per call and never stored: calling get_collection twice counts nothing twice
+            items.append(_L2Sum.apply(tuple(sc for _, sc in pending), *[v for v, _ in pending]))
+        return items
 
 
     def clear_collections():
         for v in _STORE.collections.values():
             del v[:]
         for v in _STORE.pending_l2.values():
-            del v[:]
+            v.clear()
 
 
     @contextlib.contextmanager
@@ -173,7 +175,7 @@ else:
                 torch.nn.init.trunc_normal_(t, mean=0.0, std=stddev, a=-2 * stddev, b=2 * stddev)
         var = get_variable(name, shape, initializer, device)
         if with_decay is not None:
-            _STORE.pending_l2["losses"].append((var, float(with_decay)))               # tf.nn.l2_loss * decay
+            _STORE.pending_l2["losses"][id(var)] = (var, float(with_decay))            # tf.nn.l2_loss * decay
         return var
 
 
@@ -608,7 +610,8 @@ else:
             beta = get_variable('beta', [C], lambda t: t.zero_(), device)
             moving_mean = get_variable('moving_mean', [C], lambda t: t.zero_(), device, trainable=False)
             moving_var = get_variable('moving_variance', [C], lambda t: t.fill_(1.0), device, trainable=False)
-        _STORE.pending_l2["regularization_losses"] += [(beta, 1.0), (gamma, 1.0)]
+        _STORE.pending_l2["regularization_losses"][id(beta)] = (beta, 1.0)
+        _STORE.pending_l2["regularization_losses"][id(gamma)] = (gamma, 1.0)
         return gamma, beta, moving_mean, moving_var
 
 

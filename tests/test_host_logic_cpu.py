@@ -227,3 +227,23 @@ def test_layer_oracle_closed_forms_match_autograd():
     w = rng.standard_normal((C, 5))
     gxd, gwd = OL.dense_grad(x, w, rng.standard_normal((R, 5)))
     assert gxd.shape == (R, C) and gwd.shape == (C, 5)
+
+
+def test_l2_terms_register_once_per_variable(pkg):
+    """a layer that runs many times (evaluation loops, several get_collection calls) adds its weight decay ONCE"""
+    u = pkg.sph3gcn_util
+    u.reset_variables()
+    u.clear_collections()
+    for _ in range(5):                                             # five "forward passes" over the same variable
+        with u.variable_scope("layer"):
+            w = u._variable_with_weight_decay("weights", [4, 3], 1e-3, 0.5, device="cpu")
+    store = u.get_variable_store()
+    assert len(store.pending_l2["losses"]) == 1
+    a = u.get_collection("losses")
+    b = u.get_collection("losses")                                 # a second call must not stack a second fused term
+    assert len(a) == len(b) == 1
+    want = 0.5 * 0.5 * float((w.detach() ** 2).sum())             # decay * tf.nn.l2_loss = decay * sum(w^2) / 2
+    assert abs(float(a[0]) - want) <= 1e-6 * abs(want) and abs(float(b[0]) - want) <= 1e-6 * abs(want)
+    u.clear_collections()
+    assert u.get_collection("losses") == []
+    u.reset_variables()
