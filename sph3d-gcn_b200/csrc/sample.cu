@@ -20,7 +20,7 @@
 // with k mod 1024 == tid, in ascending k, with a strict '>' scan -- the reference thread's own rule --
 // and the cross-thread rule is carried by the key (tid << 21 | k >> 10), minimised among maxima.
 #include <cooperative_groups.h>
-#include "common.cuh"
+#include "conv_common.cuh"
 #include "../../include/sph3d_b200.h"
 
 namespace cg = cooperative_groups;
@@ -119,16 +119,44 @@ fps_single_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* 
 // reads its coordinates from shared memory; (2) warp 0 pushes ONE 20-byte record per CTA into every
 // cluster CTA's shared memory (DSMEM), one cluster barrier, everybody reduces the CS records.
 // (Pushing all 32 warp records of every CTA through DSMEM instead costs 2.4 us/round; measured.)
+//
+// Round handshake (HS = true, default).  A cluster barrier costs ~2 000 cycles per round with the DSMEM stores in front
+// of it -- most of the 1.41 us round at N = 65 536 -- and release / acquire at cluster scope compiles to MEMBAR.ALL.GPU +
+// CCTL.IVALL.  Instead a record travels as TWO 16-byte vectors that each carry the round number:
+//      v0 = {distance bits, tie key, x, round}      v1 = {y, z, round, 0}
+// written with one st.shared::cluster.v4 each (a 16-byte aligned vector store reaches the peer's shared memory as one
+// transaction) and polled by the receiver with one volatile ld.shared.v4 each until both show the round number: no
+// fences, no barrier, and the polling lane already holds the record when the spin ends.  Two buffers suffice: a CTA
+// can write round j+2 into a peer only after it has read that peer's round j+1 record, which the peer sent after all
+// of its warps had finished reading round j.  The spin is bounded (a peer that never answers ends the kernel with
+// garbage instead of hanging the GPU; the parity tests would see it).  HS = false keeps the cluster barrier
+// (SPH3D_FPS_HANDSHAKE=0).
 template <int CS>
 struct ClusterSlots {
     int lbits[2][32], lkey[2][32];                      // local warp records
-    int cbits[2][CS], ckey[2][CS];                      // one record per cluster CTA (written remotely)
+    int cbits[2][CS], ckey[2][CS];                      // barrier form: one record per cluster CTA (written remotely)
     float cx[2][CS], cy[2][CS], cz[2][CS];
+    alignas(16) int4 v0[2][CS], v1[2][CS];              // handshake form
 };
 
-template <int CS, int P>
+__device__ __forceinline__ void st_peer_v4(const void* local_slot, int peer, int a, int b, int c, int d)
+{
+    const unsigned la = (unsigned)__cvta_generic_to_shared(local_slot);
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(peer));
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(ra), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ int4 ld_volatile_v4(const void* local_slot)
+{
+    const unsigned la = (unsigned)__cvta_generic_to_shared(local_slot);
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(la) : "memory");
+    return v;
+}
+
+template <int CS, int P, bool HS>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
-fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* __restrict__ out)
+fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int* __restrict__ out, int poll_all)
 {
     extern __shared__ __align__(16) float fps_smem[];
     float* lxyz = fps_smem;                             // [P*1024*3] this CTA's points, local index p*1024 + t
@@ -161,7 +189,8 @@ fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int*
     }
     float x1 = __ldg(pts), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
     if (rank == 0 && tid == 0) out[(size_t)cloud * npoint] = 0;
-    cluster.sync();                                     // peers' shared memory exists before anyone writes to it
+    if (tid < 2 * CS) { (&slots.v0[0][0])[tid] = make_int4(0, 0, 0, 0); (&slots.v1[0][0])[tid] = make_int4(0, 0, 0, 0); }
+    cluster.sync();                                     // peers' shared memory exists (and is initialised) before anyone writes to it
 
     for (int j = 1; j < npoint; j++) {
         const int buf = j & 1;
@@ -189,10 +218,45 @@ fps_cluster_kernel(int B, int N, int npoint, const float* __restrict__ xyz, int*
             const int li = ((kk >> 10) / CS) * FPS_THREADS + (kk & (FPS_THREADS - 1));
             const float wx = lxyz[3 * li], wy = lxyz[3 * li + 1], wz = lxyz[3 * li + 2];
             if (lane < CS) {
-                ClusterSlots<CS>* rs = cluster.map_shared_rank(&slots, lane);
-                rs->cbits[buf][rank] = gb; rs->ckey[buf][rank] = gk;
-                rs->cx[buf][rank] = wx; rs->cy[buf][rank] = wy; rs->cz[buf][rank] = wz;
+                if constexpr (HS) {                     // my record into slot [buf][rank] of peer `lane` (my own CTA included)
+                    st_peer_v4(&slots.v0[buf][rank], lane, gb, gk, __float_as_int(wx), j);
+                    st_peer_v4(&slots.v1[buf][rank], lane, __float_as_int(wy), __float_as_int(wz), j, 0);
+                } else {
+                    ClusterSlots<CS>* rs = cluster.map_shared_rank(&slots, lane);
+                    rs->cbits[buf][rank] = gb; rs->ckey[buf][rank] = gk;
+                    rs->cx[buf][rank] = wx; rs->cy[buf][rank] = wy; rs->cz[buf][rank] = wz;
+                }
             }
+        }
+        if constexpr (HS) {
+            int4 r0 = make_int4((int)0x80000000, 0x7fffffff, 0, 0), r1 = make_int4(0, 0, 0, 0);
+            // POLL_ALL: every warp spins on the slots itself (no second barrier, but 31 spinning warps compete for issue
+            // slots with the warps still updating distances).  Otherwise warp 0 alone spins and releases the others
+            // through a second bar.sync.
+            if (poll_all || warp == 0) {
+                int spins = 0;
+                bool ready;
+                do {                                    // lanes < CS each watch one slot of this round's buffer
+                    ready = true;
+                    if (lane < CS) {
+                        r0 = ld_volatile_v4(&slots.v0[buf][lane]);
+                        r1 = ld_volatile_v4(&slots.v1[buf][lane]);
+                        ready = (r0.w == j) && (r1.z == j);
+                    }
+                } while (!__all_sync(FULL_MASK, ready) && ++spins < (1 << 22));
+            }
+            if (!poll_all) {
+                __syncthreads();
+                if (warp != 0 && lane < CS) { r0 = ld_volatile_v4(&slots.v0[buf][lane]); r1 = ld_volatile_v4(&slots.v1[buf][lane]); }
+            }
+            int fb, fk;
+            warp_argmax(lane < CS ? r0.x : (int)0x80000000, lane < CS ? r0.y : 0x7fffffff, fb, fk);
+            const int wl = __ffs(__ballot_sync(FULL_MASK, lane < CS && r0.x == fb && r0.y == fk)) - 1;   // lowest rank among equals
+            x1 = __int_as_float(__shfl_sync(FULL_MASK, r0.z, wl));
+            y1 = __int_as_float(__shfl_sync(FULL_MASK, r1.x, wl));
+            z1 = __int_as_float(__shfl_sync(FULL_MASK, r1.y, wl));
+            if (rank == 0 && tid == 0) out[(size_t)cloud * npoint + j] = ((fk & 0x1fffff) << 10) | (fk >> 21);
+            continue;
         }
         cluster.sync();
         int fb, fk;
@@ -257,9 +321,11 @@ struct FpsPlan { int cs, p; };
 
 static FpsPlan plan_fps(int n)
 {
-    if (n <= 10 * FPS_THREADS) return FpsPlan{1, (n + FPS_THREADS - 1) / FPS_THREADS};   // single-CTA kernel
+    // clouds of up to 10 240 points: one CTA (SPH3D_FPS_CLUSTER_MIN_N lowers the switch-over point for sweeps)
+    const int single_max = tunables().fps_cluster_min_n > 0 ? tunables().fps_cluster_min_n - 1 : 10 * FPS_THREADS;
+    if (n <= single_max && n <= 10 * FPS_THREADS) return FpsPlan{1, (n + FPS_THREADS - 1) / FPS_THREADS};   // single-CTA kernel
     const int cs_opts[4] = {1, 2, 4, 8};
-    for (int i = 0; i < 4; i++) {
+    for (int i = (n <= 10 * FPS_THREADS ? 1 : 0); i < 4; i++) {
         int cs = cs_opts[i];
         int p = (n + cs * FPS_THREADS - 1) / (cs * FPS_THREADS);
         if (p <= 8) return FpsPlan{cs, p};
@@ -269,15 +335,15 @@ static FpsPlan plan_fps(int n)
     return FpsPlan{0, 0};
 }
 
-template <int CS, int P>
-static cudaError_t launch_fps(int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
+template <int CS, int P, bool HS>
+static cudaError_t launch_fps_hs(int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * CS);
     cfg.blockDim = dim3(FPS_THREADS);
     cfg.dynamicSmemBytes = (size_t)P * FPS_THREADS * 3 * sizeof(float);
-    if (cfg.dynamicSmemBytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<CS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cfg.dynamicSmemBytes + sizeof(ClusterSlots<CS>) > 48 * 1024) {      // static slots count against the 48 KB default too
+        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<CS, P, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)cfg.dynamicSmemBytes);
         if (e != cudaSuccess) return e;
     }
@@ -287,7 +353,14 @@ static cudaError_t launch_fps(int B, int N, int npoint, const float* xyz, int* o
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CS, P>, B, N, npoint, xyz, out);
+    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CS, P, HS>, B, N, npoint, xyz, out, tunables().fps_handshake == 2 ? 1 : 0);
+}
+
+template <int CS, int P>
+static cudaError_t launch_fps(int B, int N, int npoint, const float* xyz, int* out, cudaStream_t st)
+{
+    if (tunables().fps_handshake == 0) return launch_fps_hs<CS, P, false>(B, N, npoint, xyz, out, st);
+    return launch_fps_hs<CS, P, true>(B, N, npoint, xyz, out, st);
 }
 
 template <int P>
