@@ -60,7 +60,10 @@ constexpr int CELL_REACH = 2;                   // grid path when the radius spa
 // Measured (profiles/r1_nnquery_grid_vs_scan.txt): the 8-queries-per-warp scan with early exit wins up to
 // N = 10^4 (1.19 vs 1.70 ms at B=32, N=10^4, r=0.1) because the growing radius (Q1) lets most rows stop after a
 // few hundred points; the grid wins from N ~ 3*10^4 (0.96 vs 1.55 ms at B=4, N=65536, r=0.05).
-constexpr int GRID_MIN_N = 32768;               // below this the scan is faster than building + walking a grid
+// below this the scan is faster than building + walking a grid.  Round 2 (profiles/r2_nnquery.json): with the packed
+// fp32x2 scan the grid loses at every BASELINE shape, unsaturated config radii included (ModelNet level 1, r = 0.1: 1.62
+// vs 1.83 ms; cfg5, N = 65 536: 0.78 vs 0.99 ms), so it is kept for clouds beyond those (the scan grows with N^2).
+constexpr int GRID_MIN_N = 98304;
 
 struct GridInfo {
     float ox, oy, oz, inv_h;                    // cell = floor((p - o) * inv_h)

@@ -61,14 +61,18 @@ def test_cfgT_whole_batch_vs_reference_kernels_and_oracle(pkg, ref, oracle):
     _conv_both(pkg, ref, oracle, x, W, go, idx, cnt, filt, "Cfg-T B=32")
 
 
-def test_cfg5_scannet_stress_vs_reference_kernels(pkg, ref, oracle):
-    """B=4, N=65536, K=64, C=256: the grid ball query switches itself on at this size; convolution through 2 channel chunks"""
+def test_cfg5_scannet_stress_vs_reference_kernels(pkg, ref, oracle, tune):
+    """B=4, N=65536, K=64, C=256: ball query by the packed scan AND (forced) by the cell grid; convolution through 2 channel chunks"""
     B, N, K, C = 4, 65536, 64, 256
     g = torch.Generator().manual_seed(1234 + 5)
     xyz = torch.rand(B, N, 3, generator=g).to(DEV)
     r = saturating_radius(N, K)
-    assert pkg._lib.lib().sph3d_build_sphere_neighbor_workspace_bytes(B, N, N, K) > 0        # grid path is taken
     idx, cnt, dst, filt = _graph_both(pkg, ref, xyz, r, K, [8, 2, 2])
+    tune(SPH3D_NNQUERY_GRID="2")                                                             # the same graph through the grid path
+    assert pkg._lib.lib().sph3d_build_sphere_neighbor_workspace_bytes(B, N, N, K) > 0
+    gidx, gcnt, gdst = pkg.tf_nnquery.build_sphere_neighbor(xyz, xyz, radius=r, nnsample=K)
+    assert_equal(A(gidx), A(idx), "grid path nn_index"); assert_equal(A(gcnt), A(cnt)); assert_equal(A(gdst), A(dst))
+    tune(SPH3D_NNQUERY_GRID=None)
     x = torch.randn(B, N, C, generator=g).to(DEV)
     W = (0.1 * torch.randn(33, C, 1, generator=g)).to(DEV)
     go = torch.randn(B, N, C, generator=g).to(DEV)

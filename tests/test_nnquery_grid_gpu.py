@@ -57,10 +57,11 @@ def test_grid_queries_outside_the_box_and_flat_clouds(pkg, oracle, force_grid):
 
 
 def test_auto_mode_large_cloud(pkg, oracle):
-    """default policy: the grid switches itself on for N >= 32768 (cfg5-sized clouds)."""
-    N, K, r = 40000, 32, 0.04
+    """default policy: the grid switches itself on for N >= 98304 (beyond every BASELINE shape; profiles/r2_nnquery.json)."""
+    N, K, r = 100000, 32, 0.03
     xyz = make_cloud(23, 1, N, "cube")
     assert pkg._lib.lib().sph3d_build_sphere_neighbor_workspace_bytes(1, N, N, K) > 0
+    assert pkg._lib.lib().sph3d_build_sphere_neighbor_workspace_bytes(4, 65536, 65536, 64) == 0       # cfg5 scans
     oi, oc, od = oracle.build_sphere_neighbor(xyz, xyz, r, None, K)
     gi, gc, gd = pkg.tf_nnquery.build_sphere_neighbor(T(xyz), T(xyz), radius=r, nnsample=K)
     assert_equal(A(gc), oc); assert_equal(A(gi), oi); assert_equal(A(gd), od)
