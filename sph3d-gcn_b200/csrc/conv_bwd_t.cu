@@ -779,6 +779,180 @@ t_gather_kernel(unsigned rows /* B*S */, int sh, int sb, unsigned cmask, int C, 
     }
 }
 
+// ---- streaming form of the same gather: four points per warp, 32 channels per CTA column, points in degree order ----
+// The warp-per-point kernel above is bound by L2: consecutive source points share no rows, every 512-byte gather
+// misses L1 (10.5 GB through L2 at the Cfg-T unpool shape), and a point referenced by thousands of rows (the reference's
+// growing-radius ball query makes the low-index points of every cloud such hubs) keeps one warp busy long after the
+// others have finished.  Here
+//   * a CTA column handles 32 channels (blockIdx.y), so a gathered row piece is ONE 128-byte line and L1 holds four times
+//     as many rows;
+//   * a warp is four groups of eight lanes, each group streaming the list of its own point: one LDG.128 per lane fetches
+//     four different rows (four full lines), so the instruction count per edge is a quarter of the warp-per-point form;
+//   * the points of a cloud are taken in descending order of in-degree (degree_order_kernel: a counting sort into 124
+//     degree classes), 128 consecutive points per CTA round: the four lists of a warp have lengths within 25 % of each
+//     other (little lock-step padding), and the 128 lists of a round -- entries roughly ascending in the referencing row,
+//     the order in which the transposition ranked them -- sweep the same rows at the same time, which is what makes the
+//     gathers hit L1 (simulated 77-80 % with a 200 KB L1).
+// Entries are staged per group in shared memory (32 at a time: byte offset + scale), read back four steps at a time.
+// CTA shape: TQ_WARPS warps x DEPTH steps in flight per warp.  Every step of a warp is one LDG.128 (four 128-byte lines);
+// with 59 % L1 hits almost every batch of DEPTH steps waits for an L2 round trip, so the loads in flight per SM
+// (TQ_WARPS * DEPTH) decide the throughput: 32 x 4 measured 1.23 ms at the Cfg-T unpool shape (L1 pipe 42 % busy).
+
+// Work items.  A point referenced by thousands of rows would keep one lane group busy for thousands of steps while the rest
+// of the machine has finished (measured: 1.23 ms, nothing saturated), so a list is cut into PARTS of TQ_PART entries and the
+// parts of all points are the work items; partial sums of multi-part points meet in grad_input through vector reductions
+// (grad_input is zero-filled first).  Item order: part index major, points by descending degree inside a part index --
+// because the points are sorted by their number of parts, "the points that have a part j" are a PREFIX of the sorted
+// order, so item q resolves to (part j, point order[q - cum[j]]) from the small table cum[] alone.  A round of 128 items is
+// then 128 different points' j-th parts: equal lengths (no lock-step padding) over the same range of referencing rows.
+constexpr int TQ_PART = 256;
+constexpr int TQ_KEYS = 512;                                       // 32 degree classes for single-part points + parts counts
+
+// ascending in degree; single-part points: 0..31 (degree classes), others 32 + number of parts, at most pmax_cap parts
+// (a longer list -- only possible when rows repeat a neighbour -- puts its surplus into the last part)
+__device__ __forceinline__ int degree_key(int deg, int pmax_cap)
+{
+    if (deg <= TQ_PART) {
+        if (deg < 8) return deg;
+        const int e = 31 - __clz(deg);
+        return min(31, 8 + (e - 3) * 4 + ((deg >> (e - 2)) & 3));
+    }
+    return 32 + min(pmax_cap, (deg + TQ_PART - 1) / TQ_PART);      // pmax_cap <= TQ_KEYS - 33
+}
+
+// per cloud (one CTA): order[] = points by descending degree_key (counting sort), cum[j] = number of items whose part index
+// is < j (cum[0] = 0, cum[pmax] = all items), written as cum[b*(pmax_cap+1) + j]
+__global__ void __launch_bounds__(1024)
+degree_order_kernel(int S, int pmax_cap, const int* __restrict__ seg, int* __restrict__ order, int* __restrict__ cum)
+{
+    __shared__ int hist[TQ_KEYS];
+    __shared__ int start[TQ_KEYS];
+    const int b = blockIdx.x;
+    const int* sg = seg + (size_t)b * S;
+    for (int i = threadIdx.x; i < TQ_KEYS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) atomicAdd(&hist[degree_key(sg[i + 1] - sg[i], pmax_cap)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {                                        // descending key order; 512 steps, once per cloud
+        int run = 0;
+        for (int k = TQ_KEYS - 1; k >= 0; k--) { start[k] = run; run += hist[k]; }
+        // points with more than j parts: keys >= 32 + (j + 1) for j >= 1, everything for j = 0
+        int* cm = cum + (size_t)b * (pmax_cap + 1);
+        int acc = 0;
+        cm[0] = 0;
+        for (int j = 0; j < pmax_cap; j++) {
+            acc += (j == 0) ? S : start[32 + j];                   // points with more than j parts <=> key > 32 + j: sorted before it
+            cm[j + 1] = acc;
+        }
+    }
+    __syncthreads();
+    int* ord = order + (size_t)b * S;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) ord[atomicAdd(&start[degree_key(sg[i + 1] - sg[i], pmax_cap)], 1)] = i;
+}
+
+template <bool WEIGHTED, int TQ_WARPS, int DEPTH>
+__global__ void __launch_bounds__(TQ_WARPS * 32, 1)
+tq_gather_kernel(int B, int S, int C, int K, int sh, int sb, unsigned cmask, int pmax_cap, int rounds,
+                 const int* __restrict__ seg, const unsigned* __restrict__ entries, const int* __restrict__ order,
+                 const int* __restrict__ cum, const float* __restrict__ weight,
+                 const float* __restrict__ grad_output, float* __restrict__ grad_input)
+{
+    __shared__ __align__(16) unsigned sOff[TQ_WARPS][4][32];
+    __shared__ __align__(16) float sScale[TQ_WARPS][4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, l8 = lane & 7;
+    const int c0 = blockIdx.y * 32 + l8 * 4;
+    const bool chan_ok = c0 < C;                                   // C % 4 == 0 (host-checked)
+    const unsigned strideB = (unsigned)C * 4u;
+    const char* gb = reinterpret_cast<const char*>(grad_output) + (size_t)(chan_ok ? c0 : 0) * 4;
+    const int tiles = B * rounds;
+    unsigned* myOff = sOff[warp][grp];
+    float* myScale = sScale[warp][grp];
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int b = t / rounds, r = t - b * rounds;
+        const int* cm = cum + (size_t)b * (pmax_cap + 1);
+        const int total = __ldg(cm + pmax_cap);
+        if (r * (TQ_WARPS * 4) >= total) continue;                 // (CTA-uniform) this cloud has fewer rounds
+        const int q = r * (TQ_WARPS * 4) + warp * 4 + grp;        // my work item
+        int pt = -1, beg = 0, len = 0;
+        if (q < total) {
+            int lo = 0, hi = pmax_cap;                             // largest j with cum[j] <= q
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(cm + mid) <= q) lo = mid; else hi = mid;
+            }
+            pt = __ldg(order + (size_t)b * S + (q - __ldg(cm + lo)));
+            const int pbeg = __ldg(seg + (size_t)b * S + pt), pend = __ldg(seg + (size_t)b * S + pt + 1);
+            beg = pbeg + lo * TQ_PART;
+            len = (lo == pmax_cap - 1) ? pend - beg : min(TQ_PART, pend - beg);     // the last possible part takes any surplus
+        }
+        int steps = len;                                           // the warp walks max(len) steps; short groups pad with scale 0
+        steps = max(steps, __shfl_xor_sync(FULL_MASK, steps, 8));
+        steps = max(steps, __shfl_xor_sync(FULL_MASK, steps, 16));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = 0; base < steps; base += 32) {
+            // stage this group's next 32 entries: lane l8 converts entries base + 4*l8 .. + 3
+            unsigned o4[4]; float s4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = base + l8 * 4 + u;
+                o4[u] = 0u; s4[u] = 0.f;
+                if (e < len) {
+                    const unsigned ent = __ldg(entries + beg + e);
+                    const unsigned row = ent >> sh, code = (ent >> sb) & cmask;
+                    o4[u] = row * strideB;
+                    s4[u] = WEIGHTED ? __ldg(weight + (size_t)row * K + code) : 1.0f / (float)(code + 1u);
+                }
+            }
+            *reinterpret_cast<uint4*>(myOff + l8 * 4) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            *reinterpret_cast<float4*>(myScale + l8 * 4) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+            __syncwarp();
+            const int n = min(32, steps - base);
+            for (int qq = 0; qq < n; qq += DEPTH) {                // DEPTH steps = DEPTH rows per group in flight (pads: scale 0)
+                float4 v[DEPTH];
+                float sc[DEPTH];
+#pragma unroll
+                for (int d4 = 0; d4 < DEPTH; d4 += 4) {
+                    const uint4 oo = *reinterpret_cast<const uint4*>(myOff + qq + d4);
+                    const float4 ss = *reinterpret_cast<const float4*>(myScale + qq + d4);
+                    v[d4] = __ldg(reinterpret_cast<const float4*>(gb + oo.x));
+                    v[d4 + 1] = __ldg(reinterpret_cast<const float4*>(gb + oo.y));
+                    v[d4 + 2] = __ldg(reinterpret_cast<const float4*>(gb + oo.z));
+                    v[d4 + 3] = __ldg(reinterpret_cast<const float4*>(gb + oo.w));
+                    sc[d4] = ss.x; sc[d4 + 1] = ss.y; sc[d4 + 2] = ss.z; sc[d4 + 3] = ss.w;
+                }
+#pragma unroll
+                for (int d = 0; d < DEPTH; d += 2) {               // two partial sums per pair of steps shorten the FMA chain
+                    float4 a;
+                    a.x = v[d].x * sc[d]; a.y = v[d].y * sc[d]; a.z = v[d].z * sc[d]; a.w = v[d].w * sc[d];
+                    a.x = fmaf(v[d + 1].x, sc[d + 1], a.x); a.y = fmaf(v[d + 1].y, sc[d + 1], a.y);
+                    a.z = fmaf(v[d + 1].z, sc[d + 1], a.z); a.w = fmaf(v[d + 1].w, sc[d + 1], a.w);
+                    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                }
+            }
+            __syncwarp();                                          // the staging arrays are rewritten by the next refill
+        }
+        if (pt >= 0 && chan_ok && len > 0)                         // parts of one point meet in the zero-filled grad_input
+            red_add_v4(grad_input + ((size_t)b * S + pt) * C + c0, acc.x, acc.y, acc.z, acc.w);
+        __syncthreads();                                           // the CTA's warps enter the next round together
+    }
+}
+
+// scratch of the streaming form behind the plan: order[B*S] | cum[B*(pmax_cap+1)]
+struct TqGeom { int pmax_cap; long long max_items; size_t cum_off, bytes; };
+static TqGeom tq_geom(int B, int S, int R, int K)
+{
+    TqGeom q{};
+    long long pm = ((long long)R + TQ_PART - 1) / TQ_PART;         // a point is referenced at most once per row (ball queries)
+    if (pm < 1) pm = 1;
+    if (pm > TQ_KEYS - 33) pm = TQ_KEYS - 33;
+    q.pmax_cap = (int)pm;
+    q.max_items = (long long)S + ((long long)R * K + TQ_PART - 1) / TQ_PART;       // one item per point + one per full part
+    q.cum_off = align256((size_t)B * S * sizeof(int));
+    q.bytes = q.cum_off + align256((size_t)B * (q.pmax_cap + 1) * sizeof(int));
+    return q;
+}
+
 // S = source points per cloud (rows of grad_input), R = referencing rows per cloud (rows of grad_output)
 static TGeom pool_geom(int B, int S, int R, int K)
 {
@@ -793,20 +967,51 @@ size_t pool_scatter_workspace_bytes(int B, int S, int R, int C, int K)
     if (B <= 0 || S <= 0 || R <= 0 || C <= 0 || K <= 0) return 0;
     if ((long long)B * R * C * 4 >= (1LL << 32)) return 0;          // 32-bit byte offsets into grad_output
     const TGeom g = pool_geom(B, S, R, K);
-    return g.ok ? g.total : 0;
+    return g.ok ? g.total + tq_geom(B, S, R, K).bytes : 0;         // plan + degree order and item table of the streaming form
 }
 
 int pool_scatter_run(int B, int S, int R, int C, int K, const int* nn_index, const int* nn_count, const float* weight,
                      const float* grad_output, float* grad_input, void* workspace, size_t workspace_bytes, cudaStream_t st)
 {
     const TGeom g = pool_geom(B, S, R, K);
-    if (!g.ok || !workspace || workspace_bytes < g.total) return (int)cudaErrorInvalidValue;
+    if (!g.ok || !workspace || workspace_bytes < g.total + tq_geom(B, S, R, K).bytes) return (int)cudaErrorInvalidValue;
     char* plan = reinterpret_cast<char*>(workspace);
     int launches = 0;
     int rc = t_build_plan(B, S, R, 1, K, g, nn_index, nn_count, nullptr, plan, st, &launches, weight ? 1 : 0);
     if (rc) return rc;
     const int* seg = reinterpret_cast<const int*>(plan + g.seg_off);
     const unsigned* ent = reinterpret_cast<const unsigned*>(plan + g.ent_off);
+    if (C % 4 == 0 && tunables().pool_stream != 0) {               // streaming form (SPH3D_POOL_STREAM=0: warp-per-point form)
+        const TqGeom q = tq_geom(B, S, R, K);
+        int* order = reinterpret_cast<int*>(plan + g.total);
+        int* cum = reinterpret_cast<int*>(plan + g.total + q.cum_off);
+        cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)B * S * C, st);
+        if (e != cudaSuccess) return (int)e;
+        degree_order_kernel<<<B, 1024, 0, st>>>(S, q.pmax_cap, seg, order, cum);
+        SPH3D_CHECK_LAUNCH();
+        const int shape = tunables().pool_stream > 0 ? tunables().pool_stream : 328;     // warps * 10 + depth: 324, 328, 168, 1616
+        const int tq_warps = shape / 10 >= 32 ? 32 : 16;
+        const int rounds = (int)((q.max_items + tq_warps * 4 - 1) / (tq_warps * 4));
+        const long long tiles = (long long)B * rounds;
+        const int chunks = (C + 31) / 32;
+        long long want = sm_count();
+        dim3 grid((unsigned)(tiles < want ? tiles : want), (unsigned)chunks);
+        const int sh = g.sb + g.cb;
+        const unsigned cmask = (1u << g.cb) - 1u;
+#define LAUNCH_TQ(WW, DD)                                                                                                          \
+    do {                                                                                                                           \
+        if (weight) tq_gather_kernel<true, WW, DD><<<grid, WW * 32, 0, st>>>(B, S, C, K, sh, g.sb, cmask, q.pmax_cap, rounds, seg, ent, order, cum, weight, grad_output, grad_input); \
+        else tq_gather_kernel<false, WW, DD><<<grid, WW * 32, 0, st>>>(B, S, C, K, sh, g.sb, cmask, q.pmax_cap, rounds, seg, ent, order, cum, weight, grad_output, grad_input);      \
+    } while (0)
+        if (shape == 324) LAUNCH_TQ(32, 4);
+        else if (shape == 1616) LAUNCH_TQ(16, 16);
+        else if (shape == 168) LAUNCH_TQ(16, 8);
+        else LAUNCH_TQ(32, 8);
+#undef LAUNCH_TQ
+        SPH3D_CHECK_LAUNCH();
+        g_last_launch_count = launches + 2;
+        return 0;
+    }
     int vec = pick_vec_full_warp(C);
     const int chunks = (C + 32 * vec - 1) / (32 * vec);
     const unsigned rows = (unsigned)((long long)B * S);

@@ -177,6 +177,7 @@ struct Tunables {
     int bwd_algo, bwd_vec, bwd_g, bwd_threads, bwd_cta_reduce;   // SPH3D_BWD_*  (row-owned backward)
     int bwdt_threads, bwdt_depth, bwdt_g, bwdt_sort, bwdt_fold;   // SPH3D_BWDT_* (transposed backward)
     int nnquery_grid;                                    // SPH3D_NNQUERY_GRID: -1 unset, 0 never, 2 whenever possible
+    int pool_stream;                                     // SPH3D_POOL_STREAM: -1 unset = streaming gather form, 0 = warp-per-point gather form
     int fps_handshake, fps_cluster_min_n;                // SPH3D_FPS_HANDSHAKE (-1 unset = on, 0 = cluster barrier), SPH3D_FPS_CLUSTER_MIN_N
 };
 const Tunables& tunables();                              // conv_fwd.cu

@@ -50,6 +50,7 @@ static Tunables read_tunables()
     t.bwdt_sort = env_int("SPH3D_BWDT_SORT", 0);
     t.bwdt_fold = env_int("SPH3D_BWDT_FOLD", 0);
     t.nnquery_grid = env_int("SPH3D_NNQUERY_GRID", -1);
+    t.pool_stream = env_int("SPH3D_POOL_STREAM", -1);
     t.fps_handshake = env_int("SPH3D_FPS_HANDSHAKE", -1);
     t.fps_cluster_min_n = env_int("SPH3D_FPS_CLUSTER_MIN_N", 0);
     return t;
