@@ -795,8 +795,10 @@ t_gather_kernel(unsigned rows /* B*S */, int sh, int sb, unsigned cmask, int C, 
 //     gathers hit L1 (simulated 77-80 % with a 200 KB L1).
 // Entries are staged per group in shared memory (32 at a time: byte offset + scale), read back four steps at a time.
 // CTA shape: TQ_WARPS warps x DEPTH steps in flight per warp.  Every step of a warp is one LDG.128 (four 128-byte lines);
-// with 59 % L1 hits almost every batch of DEPTH steps waits for an L2 round trip, so the loads in flight per SM
-// (TQ_WARPS * DEPTH) decide the throughput: 32 x 4 measured 1.23 ms at the Cfg-T unpool shape (L1 pipe 42 % busy).
+// with ~60 % L1 hits almost every batch of DEPTH steps waits for an L2 round trip.  Measured at the Cfg-T unpool shape
+// (profiles/r2_pool_stream.json): the gather itself 0.9-1.0 ms at 32 x 8 and at 16 x 16 (L1 hit 61 %, L1 data pipe 51 %,
+// 380 M warp instructions) against 1.5 ms for the warp-per-point form; the whole gradient 1.35 ms against 1.96 ms for the
+// scatter form.  (A first 16 x 16 measurement of 0.35 ms was a launch-shape bug that skipped half of the work items.)
 
 // Work items.  A point referenced by thousands of rows would keep one lane group busy for thousands of steps while the rest
 // of the machine has finished (measured: 1.23 ms, nothing saturated), so a list is cut into PARTS of TQ_PART entries and the
@@ -989,8 +991,8 @@ int pool_scatter_run(int B, int S, int R, int C, int K, const int* nn_index, con
         if (e != cudaSuccess) return (int)e;
         degree_order_kernel<<<B, 1024, 0, st>>>(S, q.pmax_cap, seg, order, cum);
         SPH3D_CHECK_LAUNCH();
-        const int shape = tunables().pool_stream > 0 ? tunables().pool_stream : 328;     // warps * 10 + depth: 324, 328, 168, 1616
-        const int tq_warps = shape / 10 >= 32 ? 32 : 16;
+        const int shape = tunables().pool_stream > 0 ? tunables().pool_stream : 328;     // 324 / 328: 32 warps x 4 / 8 steps in flight; 168 / 1616: 16 warps x 8 / 16
+        const int tq_warps = (shape == 168 || shape == 1616) ? 16 : 32;
         const int rounds = (int)((q.max_items + tq_warps * 4 - 1) / (tq_warps * 4));
         const long long tiles = (long long)B * rounds;
         const int chunks = (C + 31) / 32;

@@ -28,8 +28,8 @@ def max_pool3d_grad(input, grad_output, max_index):
 
 
 # True: the gradient transposes the graph and gathers (no atomics); False: vector-reduction scatter (csrc/pool3d.cu).
-# Measured (profiles/r2_stage_a.json): the gather form wins only for avg-pool at Cfg-T (0.38 vs 0.49 ms); at the S3DIS
-# shapes the transposition costs more than the reductions it saves, so the scatter form stays the default.
+# Measured (profiles/r2_pool_stream.json): avg-pool has a quarter of the edges of an unpool level and the transposition
+# costs more than the reductions it saves (0.55 vs 0.49 ms at Cfg-T, 0.17 vs 0.11 ms at S3DIS): scatter stays the default.
 GATHER_FORM_GRAD = False
 
 

@@ -23,10 +23,10 @@ def _dims(input, nn_index):
     return B, nn_index.shape[1], M, C, nn_index.shape[2]
 
 
-# True: the gradients transpose the graph and gather (no atomics); False: vector-reduction scatter (csrc/pool3d.cu).
-# Measured (profiles/r2_stage_a.json): both forms are bound by the same 10 GB of L2 gather / reduction traffic (1.94 vs
-# 1.97 ms at Cfg-T, 0.65 vs 0.49 ms at the S3DIS shape), so the scatter form stays the default.
-GATHER_FORM_GRAD = False
+# True: the gradients transpose the graph and gather (streaming form: four coarse points per warp, 32-channel columns, work
+# items in order of list length; csrc/conv_bwd_t.cu); False: vector-reduction scatter (csrc/pool3d.cu).  Measured
+# (profiles/r2_pool_stream.json): 1.35 vs 1.96 ms at the Cfg-T unpool shape, 0.39 vs 0.47 ms at the S3DIS one.
+GATHER_FORM_GRAD = True
 
 
 def _scratch(B, N, M, C, K, device):
