@@ -686,6 +686,20 @@ def main():
     t1.record()
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    # the same pipeline with the kernels taken out (copies only): what the host link alone costs per step on this box,
+    # all ranks copying at once -- the e2e figure is explained by how close it sits to this floor
+    fixed = (torch.empty(B, M, C * r, device=dev), torch.empty(B, N, C, device=dev), torch.empty(F, C, r, device=dev))
+    probe = E2EPipeline(pin, ("x", "W", "go"), [(B, M, C * r), (B, N, C), (F, C, r)], lambda q: fixed)
+    for i in range(2):
+        probe.step(i)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        probe.step(i)
+    probe.drain()
+    t1.record()
+    barrier()
+    ms_copy = max_over_ranks(t0.elapsed_time(t1)) / args.steps
     # the host buffers really hold this step's results: compare with the device-resident path on the same operands
     ref_out = step().detach()
     torch.cuda.synchronize()
@@ -719,6 +733,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * B * M / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pipe.h2d, "d2h_bytes_per_step": pipe.d2h, "results_verified": e2e_ok,
+                    "copy_only_ms_per_step": ms_copy,
+                    "host_link_gbs_per_direction_all_ranks": world * pipe.h2d / (ms_copy * 1e-3) / 1e9,
                     "how": "public op on host-fed operands; every step copies features, filter and incoming gradient H2D and "
                            "3 results D2H (pinned memory, process bound to the GPU's NUMA node: %s); steps software-pipelined "
                            "over 3 streams, double buffered; graph tensors and their plan resident" % numa},
