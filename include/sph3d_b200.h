@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SPH3D_B200_ABI_VERSION 3
+#define SPH3D_B200_ABI_VERSION 4
 int sph3d_abi_version(void);
 
 /* Number of KERNELS (memsets excluded) the calling thread's most recent entry-point call enqueued (bench.py
@@ -199,6 +199,30 @@ int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
 size_t sph3d_dense_gemm_workspace_bytes(int op, int M, int N, int K, int L);
 int sph3d_dense_gemm(int op, int M, int N, int K, int L, const float* A, const float* B, float* D,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- N2: the separable layer as one kernel, utils/sph3gcn_util.py:128-161 (separable_conv3d) --------------------------
+ * depthwise_conv3d (tf_conv3d_gpu.cu:7-29) -> tf.matmul with the pointwise weights -> bias_add -> elu -> per-channel
+ * affine, fused (csrc/sepconv.cu, hand-written tcgen05): the (B, M, C*r) depthwise result goes from the gathering warps
+ * into the tensor core's shared-memory operand and never to memory, unless depthwise_out != NULL (training keeps it for
+ * the weight gradient; it is then bit-identical to sph3d_depthwise_conv3d's output).
+ *   output (B*M, Cout) = act(depthwise(input) * W + bias) * scale + shift      act: 0 = none, 1 = ELU
+ *   bias / scale / shift: Cout floats each or NULL (inference-mode batch normalisation folds into scale / shift:
+ *   scale = gamma * invstd, shift = beta - moving_mean * scale; NULL, NULL, NULL, act 0 returns the raw product for the
+ *   training-mode layer tail sph3d_bias_act_bn).
+ *   weight_image: the pointwise weights W (C*r x Cout, fp32 row-major) re-packed by sph3d_sepconv_pack_weights into
+ *   sph3d_sepconv_weight_image_bytes(C*r, Cout) bytes (three bf16 terms per weight in the tensor core's operand
+ *   layout); re-pack whenever W changes.  fp32 accuracy: every cross term down to 2^-24 of a product is accumulated.
+ * sph3d_separable_conv3d_supported: 1 where the fused kernel applies (r in {1,2}, C*r <= 128, C a full-warp strip of 2 or
+ * 4 floats per lane, Cout <= 256, F <= 128); elsewhere the caller composes the three ops.  Arguments up to `filter` are
+ * sph3d_depthwise_conv3d's. */
+int sph3d_separable_conv3d_supported(int B, int N, int M, int F, int C, int r, int K, int Cout);
+size_t sph3d_sepconv_weight_image_bytes(int Cr, int Cout);
+int sph3d_sepconv_pack_weights(int Cr, int Cout, const float* weights, void* weight_image, void* stream);
+int sph3d_separable_conv3d(int B, int N, int M, int F, int C, int r, int K, int Cout,
+                           const int* nn_index, const int* nn_count, const int* bin_index,
+                           const float* input, const float* filter, const void* weight_image,
+                           const float* bias, const float* scale, const float* shift, int act,
+                           float* depthwise_out, float* output, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,10 @@ SIGNATURES = {
     "sph3d_bias_act_bn_grad": (c_int, [c_int] * 4 + [_P] * 11 + [c_size_t, _P]),
     "sph3d_dense_gemm_workspace_bytes": (c_size_t, [c_int] * 5),
     "sph3d_dense_gemm": (c_int, [c_int] * 5 + [_P] * 4 + [c_size_t, _P]),
+    "sph3d_separable_conv3d_supported": (c_int, [c_int] * 8),
+    "sph3d_sepconv_weight_image_bytes": (c_size_t, [c_int] * 2),
+    "sph3d_sepconv_pack_weights": (c_int, [c_int] * 2 + [_P] * 3),
+    "sph3d_separable_conv3d": (c_int, [c_int] * 8 + [_P] * 9 + [c_int] + [_P] * 3),
 }
 
 
@@ -85,7 +89,7 @@ def lib():
         fn = getattr(handle, name)      # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if handle.sph3d_abi_version() != 3:
+    if handle.sph3d_abi_version() != 4:
         raise ImportError("sph3d-gcn_b200: ABI version mismatch in %s" % path)
     _LIB = handle
     return _LIB

@@ -15,8 +15,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsph3d_b200.so")
 SOURCES = ["nnquery.cu", "buildkernel.cu", "conv_fwd.cu", "conv_bwd.cu", "conv_bwd_t.cu", "pool3d.cu", "sample.cu", "post.cu",
+           "sepconv.cu",
            "dense_nn.cu", "dense_nt.cu", "dense_tn.cu", "dense_nn2.cu", "dense_nt2.cu", "dense_abi.cu"]
-HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", "dense_gemm.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
+HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", "tc05.cuh", "dense_gemm.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

@@ -205,6 +205,23 @@ def _use_planned(C, r, rows):
     return r == 1 or (r == 2 and C * r <= 512 and rows >= 4096)
 
 
+def backward_on_graph(input, filter, grad_output, graph):
+    """(grad_input, grad_filter) for the graph tensor OBJECTS `graph` = (nn_index, nn_count, bin_index): the planned form
+    when the shape pays and a transposed graph hangs off (or can be hung on) bin_index, else the one-call gradient."""
+    g_idx, g_cnt, g_bin = graph
+    grad_output = grad_output.contiguous()
+    F, C, r = filter.shape
+    if SHARE_PLANS and _use_planned(C, r, input.shape[0] * g_idx.shape[1]):
+        L = _lib.lib()
+        B, N = input.shape[0], input.shape[1]
+        M, K = g_idx.shape[1], g_idx.shape[2]
+        if L.sph3d_depthwise_conv3d_grad_planned_workspace_bytes(B, N, M, F, C, r, K) > 0:
+            plan = _shared_plan("bwd", g_idx, g_cnt, g_bin, F, N)
+            if plan is not None:
+                return depthwise_conv3d_grad_planned(input, filter, grad_output, g_cnt, plan, K)
+    return depthwise_conv3d_grad(input, filter, grad_output, g_idx, g_cnt, g_bin)
+
+
 class _DepthwiseConv3d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, filter, nn_index, nn_count, bin_index):
@@ -214,20 +231,8 @@ class _DepthwiseConv3d(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        input, filter, nn_index, nn_count, bin_index = ctx.saved_tensors
-        grad_output = grad_output.contiguous()
-        F, C, r = filter.shape
-        if SHARE_PLANS and _use_planned(C, r, input.shape[0] * ctx.graph[0].shape[1]):
-            g_idx, g_cnt, g_bin = ctx.graph
-            L = _lib.lib()
-            B, N = input.shape[0], input.shape[1]
-            M, K = g_idx.shape[1], g_idx.shape[2]
-            if L.sph3d_depthwise_conv3d_grad_planned_workspace_bytes(B, N, M, F, C, r, K) > 0:
-                plan = _shared_plan("bwd", g_idx, g_cnt, g_bin, F, N)
-                if plan is not None:
-                    gi, gf = depthwise_conv3d_grad_planned(input, filter, grad_output, g_cnt, plan, K)
-                    return gi, gf, None, None, None
-        gi, gf = depthwise_conv3d_grad(input, filter, grad_output, nn_index, nn_count, bin_index)
+        input, filter = ctx.saved_tensors[:2]
+        gi, gf = backward_on_graph(input, filter, grad_output, ctx.graph)
         return gi, gf, None, None, None
 
 

@@ -34,7 +34,7 @@ if __package__ in (None, ""):           # flat import from sys.path, the way the
     _pkg = importlib.import_module("sph3d_gcn_b200")
     sys.modules[__name__] = _pkg.utils.sph3gcn_util
 else:
-    from ..tf_ops import tf_conv3d, tf_pool3d, tf_unpool3d
+    from ..tf_ops import tf_conv3d, tf_pool3d, tf_unpool3d, tf_sepconv
     from . import layer_tail
     from ..tf_ops.tf_nnquery import build_sphere_neighbor, build_cube_neighbor
     from ..tf_ops.tf_sample import farthest_point_sample, inverse_density_sample, random_sample
@@ -451,6 +451,67 @@ else:
         return _Dense.apply(x2d.contiguous(), w.contiguous())
 
 
+    # The separable layer as one kernel (csrc/sepconv.cu, row N2 of SURVEY.md section 8f): the depthwise result goes from
+    # the gathering warps straight into the tensor core's operand and the pointwise product (and, without gradients, the
+    # whole bias -> ELU -> folded-BN tail) happens before anything is written.  With gradients the depthwise result is
+    # also kept (the weight gradient needs it) and the raw product feeds the training-mode layer tail.
+    FUSE_SEPARABLE = True
+
+
+    class _SeparableFused(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index):
+            out, dw = tf_sepconv.separable_conv3d(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index,
+                                                  keep_depthwise=True)
+            ctx.save_for_backward(inputs, depthwise_kernel, kernel, dw)
+            ctx.graph = (nn_index, nn_count, filt_index)      # the tensor OBJECTS (a shared plan hangs off filt_index)
+            return out
+
+        @staticmethod
+        def backward(ctx, g):
+            inputs, depthwise_kernel, kernel, dw = ctx.saved_tensors
+            B, M, cout = g.shape
+            kp = kernel.shape[0]
+            g2 = g.contiguous().reshape(-1, cout)
+            gw = _weight_grad(dw.reshape(-1, kp), g2) if ctx.needs_input_grad[2] else None
+            gi = gf = None
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                gdw = _tc_gemm(1, g2, kernel, g2.shape[0], kp, cout) if _tc_pays(g2.shape[0], kp) else None
+                if gdw is None:
+                    gdw = g2 @ kernel.t()
+                gi, gf = tf_conv3d.backward_on_graph(inputs, depthwise_kernel, gdw.reshape(B, M, kp), ctx.graph)
+            return gi, gf, gw, None, None, None
+
+
+    def _fused_separable(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index, num_out_channels,
+                         activation_fn, with_bn, with_bias, reuse, is_training):
+        """the fused route of separable_conv3d, or None when the composition has to run"""
+        if not (FUSE_SEPARABLE and inputs.is_cuda and tf_sepconv.supported(inputs, depthwise_kernel, nn_index,
+                                                                         num_out_channels)):
+            return None
+        inputs, depthwise_kernel, kernel = inputs.contiguous(), depthwise_kernel.contiguous(), kernel.contiguous()
+        needs_grad = torch.is_grad_enabled() and (inputs.requires_grad or depthwise_kernel.requires_grad or
+                                                  kernel.requires_grad)
+        tail_folds = (activation_fn is None or activation_fn is elu) and not (with_bn and _as_bool(is_training))
+        if needs_grad or not (FUSED_TAIL and tail_folds):
+            if needs_grad:
+                outputs = _SeparableFused.apply(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index)
+            else:
+                outputs, _ = tf_sepconv.separable_conv3d(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index)
+            return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
+        # inference: the whole tail rides in the epilogue (variables are created in _post's order)
+        biases = _zeros_variable('biases', [num_out_channels], inputs.device) if with_bias else None
+        scale = shift = None
+        if with_bn:
+            gamma, beta, moving_mean, moving_var = _bn_variables(num_out_channels, inputs.device, 'bn', reuse)
+            scale = gamma * torch.rsqrt(moving_var + BN_EPSILON)
+            shift = beta - moving_mean * scale
+        act = tf_sepconv.ACT_ELU if activation_fn is elu else tf_sepconv.ACT_NONE
+        outputs, _ = tf_sepconv.separable_conv3d(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index,
+                                                 bias=biases, scale=scale, shift=shift, act=act)
+        return outputs
+
+
     # bias -> activation -> BN run as ONE op (csrc/post.cu) whenever the activation is the library's elu or None;
     # any other callable keeps the node-by-node composition.  FUSED_TAIL = False forces the composition (A/B runs).
     FUSED_TAIL = True
@@ -507,12 +568,8 @@ else:
             # the 16-byte-vector kernels.  The VARIABLES keep the reference's shapes.
             pad = (-num_in_channels) % 4
             if pad:
-                outputs = tf_conv3d.depthwise_conv3d(F.pad(inputs, (0, pad)), F.pad(depthwise_kernel, (0, 0, 0, pad)),
-                                                     nn_index, nn_count, filt_index)
-            else:
-                outputs = tf_conv3d.depthwise_conv3d(inputs, depthwise_kernel, nn_index, nn_count, filt_index)
-
-            batch_size = outputs.shape[0]
+                inputs, depthwise_kernel = F.pad(inputs, (0, pad)), F.pad(depthwise_kernel, (0, 0, 0, pad))
+            batch_size = inputs.shape[0]
             num_in_channels = num_in_channels * depth_multiplier
             kernel = _variable_with_weight_decay('weights', shape=[num_in_channels, num_out_channels],
                                                  use_xavier=use_xavier, stddev=stddev,
@@ -520,6 +577,11 @@ else:
             if pad:
                 kernel = F.pad(kernel, (0, 0, 0, pad * depth_multiplier))
                 num_in_channels += pad * depth_multiplier
+            fused = _fused_separable(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index, num_out_channels,
+                                     activation_fn, with_bn, with_bias, reuse, is_training)
+            if fused is not None:
+                return fused
+            outputs = tf_conv3d.depthwise_conv3d(inputs, depthwise_kernel, nn_index, nn_count, filt_index)
             outputs = _dense(outputs.reshape(-1, num_in_channels), kernel)
             outputs = outputs.reshape(batch_size, -1, num_out_channels)
             return _post(outputs, num_out_channels, activation_fn, with_bn, with_bias, reuse, is_training)
