@@ -212,8 +212,8 @@ int sph3d_dense_gemm(int op, int M, int N, int K, int L, const float* A, const f
  *   weight_image: the pointwise weights W (C*r x Cout, fp32 row-major) re-packed by sph3d_sepconv_pack_weights into
  *   sph3d_sepconv_weight_image_bytes(C*r, Cout) bytes (three bf16 terms per weight in the tensor core's operand
  *   layout); re-pack whenever W changes.  fp32 accuracy: every cross term down to 2^-24 of a product is accumulated.
- * sph3d_separable_conv3d_supported: 1 where the fused kernel applies (r in {1,2}, C*r <= 128, C a full-warp strip of 2 or
- * 4 floats per lane, Cout <= 256, F <= 128); elsewhere the caller composes the three ops.  Arguments up to `filter` are
+ * sph3d_separable_conv3d_supported: 1 where the fused kernel applies (r in {1,2}, C <= 128 and even, C*r <= 256,
+ * Cout <= 256, F <= 128); elsewhere the caller composes the three ops.  Arguments up to `filter` are
  * sph3d_depthwise_conv3d's. */
 int sph3d_separable_conv3d_supported(int B, int N, int M, int F, int C, int r, int K, int Cout);
 size_t sph3d_sepconv_weight_image_bytes(int Cr, int Cout);

@@ -65,7 +65,8 @@ def timing():
     rows = []
     s3g = S.utils.sph3gcn_util
     for name, B, N, K, C, r, cout in [("cfgT", 32, 10000, 64, 128, 1, 128), ("s3dis_l1", 8, 8192, 64, 64, 2, 64),
-                                      ("s3dis_l1_o128", 8, 8192, 64, 64, 2, 128), ("modelnet_l1b", 32, 10000, 64, 64, 1, 64)]:
+                                      ("s3dis_l1_o128", 8, 8192, 64, 64, 2, 128), ("s3dis_l1b_c128_r2", 8, 8192, 64, 128, 2, 128),
+                                      ("modelnet_l1b", 32, 10000, 64, 64, 1, 64)]:
         g = torch.Generator().manual_seed(7)
         xyz = torch.rand((B, N, 3), generator=g).to(DEV)
         radius = float((3.0 * 2 * K / (4.0 * np.pi * N)) ** (1.0 / 3.0))

@@ -179,6 +179,8 @@ struct Tunables {
     int nnquery_grid;                                    // SPH3D_NNQUERY_GRID: -1 unset, 0 never, 2 whenever possible
     int pool_stream;                                     // SPH3D_POOL_STREAM: -1 unset = streaming gather form, 0 = warp-per-point gather form
     int fps_handshake, fps_cluster_min_n;                // SPH3D_FPS_HANDSHAKE (-1 unset = on, 0 = cluster barrier), SPH3D_FPS_CLUSTER_MIN_N
+    int fwd_smem_pad_kb;                                 // SPH3D_FWD_SMEM_PAD_KB: unused shared memory added to the forward kernel (shrinks its L1: the sensitivity sweep of DESIGN 4.10)
+    int sepconv_tile, sepconv_stages;                    // SPH3D_SEPCONV_TILE (64 / 32 rows), SPH3D_SEPCONV_STAGES (weight ring depth)
 };
 const Tunables& tunables();                              // conv_fwd.cu
 static inline int tun(int v, int dflt) { return v > 0 ? v : dflt; }

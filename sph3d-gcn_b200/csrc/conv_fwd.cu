@@ -53,6 +53,9 @@ static Tunables read_tunables()
     t.pool_stream = env_int("SPH3D_POOL_STREAM", -1);
     t.fps_handshake = env_int("SPH3D_FPS_HANDSHAKE", -1);
     t.fps_cluster_min_n = env_int("SPH3D_FPS_CLUSTER_MIN_N", 0);
+    t.fwd_smem_pad_kb = env_int("SPH3D_FWD_SMEM_PAD_KB", 0);
+    t.sepconv_tile = env_int("SPH3D_SEPCONV_TILE", 0);
+    t.sepconv_stages = env_int("SPH3D_SEPCONV_STAGES", 0);
     return t;
 }
 static Tunables g_tunables = read_tunables();             // once, at library load
@@ -274,6 +277,8 @@ static ConvPlan plan_fwd(int B, int N, int M, int F, int C, int r, bool planned)
     while (smem + sort_bytes > SMEM_CAP && vec > 1) { vec >>= 1; smem >>= 1; }
     if (smem + sort_bytes > SMEM_CAP) return p;
     smem += sort_bytes;
+    if (tunables().fwd_smem_pad_kb > 0 && smem + (size_t)tunables().fwd_smem_pad_kb * 1024 <= SMEM_CAP)
+        smem += (size_t)tunables().fwd_smem_pad_kb * 1024;        // sensitivity sweep only: the pad is never touched
     p.vec = vec; p.smem = smem;
     p.chunks = (C + 32 * vec - 1) / (32 * vec);
     const long long rows = (long long)B * M;

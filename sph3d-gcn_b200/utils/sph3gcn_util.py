@@ -454,8 +454,13 @@ else:
     # The separable layer as one kernel (csrc/sepconv.cu, row N2 of SURVEY.md section 8f): the depthwise result goes from
     # the gathering warps straight into the tensor core's operand and the pointwise product (and, without gradients, the
     # whole bias -> ELU -> folded-BN tail) happens before anything is written.  With gradients the depthwise result is
-    # also kept (the weight gradient needs it) and the raw product feeds the training-mode layer tail.
+    # also kept (the weight gradient needs it) and the raw product feeds the training-mode layer tail.  Measured
+    # (profiles/r2_sepconv.json, B200): without gradients the fused layer is 1.2-1.3x faster than the composition
+    # (0.79 vs 1.01 ms at B=32, N=10^4, K=64, C=128 -> 128); with gradients it is 3-8 % slower than depthwise + product as
+    # two kernels (0.78 vs 0.73 ms: the kernel is issue-bound and the operand staging adds instructions to the gather
+    # loop's warps), so training keeps the composition unless FUSE_SEPARABLE_TRAINING is set.
     FUSE_SEPARABLE = True
+    FUSE_SEPARABLE_TRAINING = False
 
 
     class _SeparableFused(torch.autograd.Function):
@@ -493,6 +498,8 @@ else:
         needs_grad = torch.is_grad_enabled() and (inputs.requires_grad or depthwise_kernel.requires_grad or
                                                   kernel.requires_grad)
         tail_folds = (activation_fn is None or activation_fn is elu) and not (with_bn and _as_bool(is_training))
+        if (needs_grad or not (FUSED_TAIL and tail_folds)) and not FUSE_SEPARABLE_TRAINING:
+            return None
         if needs_grad or not (FUSED_TAIL and tail_folds):
             if needs_grad:
                 outputs = _SeparableFused.apply(inputs, depthwise_kernel, kernel, nn_index, nn_count, filt_index)

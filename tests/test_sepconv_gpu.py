@@ -57,6 +57,9 @@ CASES = [
     ("c128_r1_o13_odd_outputs", 2, 500, 32, 128, 1, 13, True, False, 0),
     ("many_tiles_per_cta", 4, 6000, 16, 64, 2, 128, True, True, 1),
     ("tiny_one_partial_tile", 1, 37, 8, 128, 1, 64, False, False, 1),
+    ("s3dis_l1b_c128_r2_o128_tiles_of_32", 2, 1100, 64, 128, 2, 128, True, True, 1),
+    ("c128_r2_o256_two_blocks", 1, 900, 32, 128, 2, 256, True, False, 1),
+    ("c96_r2_o200_three_chunks", 2, 700, 32, 96, 2, 200, False, True, 0),
 ]
 
 
@@ -105,7 +108,8 @@ def test_fused_layer_vs_oracle(case, pkg, oracle):
 def test_unsupported_shapes_are_refused(pkg):
     L = pkg._lib.lib()
     assert L.sph3d_separable_conv3d_supported(2, 1000, 1000, 33, 128, 1, 64, 128) == 1
-    assert L.sph3d_separable_conv3d_supported(2, 1000, 1000, 33, 128, 2, 64, 128) == 0      # C*r = 256
+    assert L.sph3d_separable_conv3d_supported(2, 1000, 1000, 33, 128, 2, 64, 128) == 1      # C*r = 256: tiles of 32 points
+    assert L.sph3d_separable_conv3d_supported(2, 1000, 1000, 33, 256, 1, 64, 128) == 0      # two channel chunks
     assert L.sph3d_separable_conv3d_supported(2, 1000, 1000, 33, 64, 3, 64, 128) == 0       # multiplier 3
     assert L.sph3d_separable_conv3d_supported(2, 1000, 1000, 33, 64, 1, 64, 512) == 0       # Cout > 256
     x = torch.zeros(1, 10, 256, device=DEV)
@@ -132,8 +136,8 @@ def test_layer_routes_through_the_fused_kernel_and_matches_the_composition(train
         s3g.reset_variables()
         s3g.clear_collections()
         torch.manual_seed(5)
-        old = s3g.FUSE_SEPARABLE
-        s3g.FUSE_SEPARABLE = fuse
+        old = s3g.FUSE_SEPARABLE, s3g.FUSE_SEPARABLE_TRAINING
+        s3g.FUSE_SEPARABLE = s3g.FUSE_SEPARABLE_TRAINING = fuse
         try:
             xt = T(x).requires_grad_(training)
             with torch.set_grad_enabled(training):
@@ -148,7 +152,7 @@ def test_layer_routes_through_the_fused_kernel_and_matches_the_composition(train
             names = list(s3g.named_variables())
             return A(out), grads, names, launches
         finally:
-            s3g.FUSE_SEPARABLE = old
+            s3g.FUSE_SEPARABLE, s3g.FUSE_SEPARABLE_TRAINING = old
 
     out_f, grads_f, names_f, _ = run(True)
     out_c, grads_c, names_c, _ = run(False)
