@@ -224,6 +224,25 @@ int sph3d_separable_conv3d(int B, int N, int M, int F, int C, int r, int K, int 
                            const float* bias, const float* scale, const float* shift, int act,
                            float* depthwise_out, float* output, void* stream);
 
+/* ---- a12 (pointwise product, hand-written): y (R x N) = x (R x K) * W, utils/sph3gcn_util.py:144-146, :203-205, :254-256
+ * csrc/rowsgemm.cu: the rows stream through HBM once as fp32, are split into three bf16 terms in registers and written
+ * straight into the tensor core's shared-memory operand; six cross products per k-step (everything down to 2^-24 of a
+ * product) accumulate in tensor memory (tcgen05.mma, one issuing thread), four epilogue warps store the finished tile while
+ * the next one is produced.  No template library.
+ *   image: the weights re-packed by sph3d_rows_gemm_pack into sph3d_rows_gemm_image_bytes(K, N) bytes (three bf16 terms in
+ *   the operand's swizzled layout).  trans = 0: weights is (K x N) row-major (y = x * W); trans = 1: weights is (N x K)
+ *   row-major (y = x * W^T: the input gradient gx = g * w^T of the same layer packs w with trans = 1).
+ *   terms: bf16 terms per operand.  3 = the six cross products down to 2^-24 of a product; 2 = the four products of
+ *   hi + mid, every dropped term below 2^-17 of a product (the rounding of an fp32 dot product of 128 terms is of that
+ *   size), two thirds of the tensor-core work and of the operand traffic.
+ *   K and N multiples of 4, x / y / image 16-byte aligned, else cudaErrorInvalidValue (1). */
+size_t sph3d_rows_gemm_image_bytes(int K, int N);
+int sph3d_rows_gemm_pack(int K, int N, const float* weights, int trans, void* image, void* stream);
+int sph3d_rows_gemm(int R, int K, int N, int terms, const float* x, const void* image, float* y, void* stream);
+/* diagnostics: while `buffer` (6*64*4 int64 of device memory) is set, CTA (0,0) of every sph3d_rows_gemm launch records
+ * clock64 stamps of its producer / issuer / epilogue steps there; NULL switches it off (the default). */
+void sph3d_rows_gemm_trace(void* buffer);
+
 #ifdef __cplusplus
 }
 #endif

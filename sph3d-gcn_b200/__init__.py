@@ -16,12 +16,12 @@ There is no CPU path: every op requires CUDA tensors and the compiled library.
 """
 from . import build as _build_mod                      # noqa: F401
 from . import _lib                                     # noqa: F401
-from .tf_ops import tf_nnquery, tf_buildkernel, tf_conv3d, tf_sample, tf_pool3d, tf_unpool3d, tf_sepconv  # noqa: F401
+from .tf_ops import tf_nnquery, tf_buildkernel, tf_conv3d, tf_sample, tf_pool3d, tf_unpool3d, tf_sepconv, tf_rowsgemm  # noqa: F401
 from .utils import sph3gcn_util                        # noqa: F401
 from . import models                                   # noqa: F401
 from . import io                                       # noqa: F401
 
 build = _build_mod.build
 library_path = _lib.library_path
-__all__ = ["tf_nnquery", "tf_buildkernel", "tf_conv3d", "tf_sample", "tf_pool3d", "tf_unpool3d", "tf_sepconv",
+__all__ = ["tf_nnquery", "tf_buildkernel", "tf_conv3d", "tf_sample", "tf_pool3d", "tf_unpool3d", "tf_sepconv", "tf_rowsgemm",
            "sph3gcn_util", "models", "io", "build", "library_path"]

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsph3d_b200.so")
 SOURCES = ["nnquery.cu", "buildkernel.cu", "conv_fwd.cu", "conv_bwd.cu", "conv_bwd_t.cu", "pool3d.cu", "sample.cu", "post.cu",
-           "sepconv.cu",
+           "sepconv.cu", "rowsgemm.cu",
            "dense_nn.cu", "dense_nt.cu", "dense_tn.cu", "dense_nn2.cu", "dense_nt2.cu", "dense_abi.cu"]
 HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", "tc05.cuh", "dense_gemm.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -81,19 +81,28 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA translation unit for sm_100a and link the shared library."""
+    """Compile every CUDA translation unit for sm_100a and link the shared library.  Objects are kept under lib/obj
+    (git-ignored) so that only the translation units older than their source or any header are recompiled."""
     if not force and not is_stale():
         return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    def deps_time(source):
+        # the CUTLASS instantiations (two minutes each) include nothing of this library but dense_gemm.cuh
+        hdrs = ["dense_gemm.cuh"] if source.startswith("dense_") and source != "dense_abi.cu" else HEADERS
+        return _newest([os.path.normpath(os.path.join(CSRC, h)) for h in hdrs] + [os.path.join(CSRC, source)])
     objs = []
     procs = []
     for s in SOURCES:
-        obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + _extra_flags(s) + ["-c", "-o", obj, os.path.join(CSRC, s)]
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        objs.append(obj)
+        src = os.path.join(CSRC, s)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= deps_time(s):
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + _extra_flags(s) + ["-c", "-o", obj, src]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-        objs.append(obj)
     for cmd, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
@@ -102,8 +111,6 @@ def build(force=False, verbose=False):
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(link), r.stdout.decode(errors="replace")))
-    for o in objs:
-        os.remove(o)
     return LIB
 
 

@@ -109,6 +109,34 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-uniform issue.  Inside `if (lane == 0)` the compiler treats the descriptors as per-lane values: every UTCHMMA is
+// wrapped in an ELECT / BRA.U.ANY loop behind R2UR moves and four uniform ALU operations that rebuild the descriptor
+// (~13 dependent instructions of ONE warp per MMA = more cycles than the 64 the tensor core needs for a 128 x 128 x 16
+// product; measured in rowsgemm.cu: 135 cycles per MMA).  Here the whole warp runs the loop with warp-uniform values,
+// one elected lane executes the instruction, and a k-step only adds 2 to the low descriptor word (32 bytes >> 4).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t SMEM_DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+// D[tmem] (+)= A * B with the descriptors given by their low words (high word = SMEM_DESC_HI_SW128); whole-warp call,
+// one elected lane issues
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate)
+{
+    if (elect_one())
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                     :: "r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(SMEM_DESC_HI_SW128) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar)
+{
+    if (elect_one())
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
 // the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -128,6 +156,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+
+// 32 consecutive columns WITHOUT the wait: several loads can be queued before one tmem_ld_wait().  (A tcgen05.ld issued
+// while tcgen05.mma instructions are queued completes only ~1 300 cycles later -- measured in rowsgemm.cu with clock64
+// stamps -- so an epilogue that waits after every 16 columns pays that latency eight times per accumulator.)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 8 / 4 consecutive columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])

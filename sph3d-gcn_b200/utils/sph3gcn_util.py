@@ -34,7 +34,7 @@ if __package__ in (None, ""):           # flat import from sys.path, the way the
     _pkg = importlib.import_module("sph3d_gcn_b200")
     sys.modules[__name__] = _pkg.utils.sph3gcn_util
 else:
-    from ..tf_ops import tf_conv3d, tf_pool3d, tf_unpool3d, tf_sepconv
+    from ..tf_ops import tf_conv3d, tf_pool3d, tf_unpool3d, tf_sepconv, tf_rowsgemm
     from . import layer_tail
     from ..tf_ops.tf_nnquery import build_sphere_neighbor, build_cube_neighbor
     from ..tf_ops.tf_sample import farthest_point_sample, inverse_density_sample, random_sample
@@ -424,12 +424,34 @@ else:
         return out
 
 
+    # y = x w and gx = g w^T on the hand-written tcgen05 rows product (csrc/rowsgemm.cu; the weights are re-packed per call
+    # into the tensor core's operand image, the rows cross HBM once as fp32).  Measured on the layer shapes of the three
+    # networks (profiles/r2_rowsgemm.json): 1.3-1.9x the CUTLASS 9xBF16 instantiation it replaces and 2-2.8x the fp32
+    # library GEMM from 3 072 rows up; below ~1 000 rows the launch is the cost and the library GEMM stays.
+    ROWS_GEMM = True
+    ROWS_GEMM_MIN_ROWS = 1024
+    ROWS_GEMM_TERMS = 3            # 3: six cross products (error 1-2e-6 of the terms); 2: four (2-5e-6), ~1.25x faster
+
+
+    def _rows_gemm(x, w, trans):
+        """x @ w (trans False) or x @ w.T (trans True) through sph3d_rows_gemm; None when the shape is not covered"""
+        if not (ROWS_GEMM and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32):
+            return None
+        R, K = x.shape
+        N = w.shape[0] if trans else w.shape[1]
+        if R < ROWS_GEMM_MIN_ROWS or K % 4 or N % 4 or x.data_ptr() % 16:
+            return None
+        return tf_rowsgemm.rows_gemm(x, w, trans=trans, terms=ROWS_GEMM_TERMS)
+
+
     class _Dense(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, w):
             ctx.save_for_backward(x, w)
             R, K = x.shape
-            y = _tc_gemm(0, x, w, R, w.shape[1], K) if _tc_pays(R, w.shape[1]) else None
+            y = _rows_gemm(x, w, False)
+            if y is None and _tc_pays(R, w.shape[1]):
+                y = _tc_gemm(0, x, w, R, w.shape[1], K)
             return y if y is not None else x @ w
 
         @staticmethod
@@ -439,7 +461,9 @@ else:
             gx = gw = None
             if ctx.needs_input_grad[0]:
                 R, N = g.shape
-                gx = _tc_gemm(1, g, w, R, w.shape[0], N) if _tc_pays(R, w.shape[0]) else None
+                gx = _rows_gemm(g, w, True)
+                if gx is None and _tc_pays(R, w.shape[0]):
+                    gx = _tc_gemm(1, g, w, R, w.shape[0], N)
                 if gx is None:
                     gx = g @ w.t()
             if ctx.needs_input_grad[1]:
