@@ -187,19 +187,6 @@ int sph3d_bias_act_bn_grad(int R, int C, int act, int training,
                            float* grad_x, float* grad_bias, float* grad_gamma, float* grad_beta,
                            void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- a12 (pointwise product): tf.matmul over the B*M rows, utils/sph3gcn_util.py:144-146, :203-205, :254-256 --------
- * fp32 in, fp32 out, fp32 accuracy, on tcgen05 tensor cores: each operand tile is split on chip into three BF16 terms and
- * all nine cross products are accumulated in TMEM (csrc/dense_gemm.cuh).  D[l] (M x N, row-major, packed over l < L) =
- *   op 0:  A[l] (M x K row-major) * B[l] (K x N row-major)                       y  = x * w
- *   op 1:  A[l] (M x K row-major) * B[l]^T with B[l] (N x K row-major)           gx = g * w^T
- *   op 2:  A[l]^T with A[l] (K x M row-major) * B[l] (K x N row-major)           gw = x^T * g, L = row slabs (split-K)
- *   op 3 / 4: ops 0 / 1 with cta_group::2 (a CTA pair per 256 x 128 tile)
- * M, N, K multiples of 4 and 16-byte aligned pointers (TMA), else cudaErrorInvalidValue (1): the caller keeps such shapes
- * on its library GEMM.  Returns cudaErrorNotSupported (801) when the library was built without the CUTLASS header tree. */
-size_t sph3d_dense_gemm_workspace_bytes(int op, int M, int N, int K, int L);
-int sph3d_dense_gemm(int op, int M, int N, int K, int L, const float* A, const float* B, float* D,
-                     void* workspace, size_t workspace_bytes, void* stream);
-
 /* ---- N2: the separable layer as one kernel, utils/sph3gcn_util.py:128-161 (separable_conv3d) --------------------------
  * depthwise_conv3d (tf_conv3d_gpu.cu:7-29) -> tf.matmul with the pointwise weights -> bias_add -> elu -> per-channel
  * affine, fused (csrc/sepconv.cu, hand-written tcgen05): the (B, M, C*r) depthwise result goes from the gathering warps
@@ -239,6 +226,13 @@ int sph3d_separable_conv3d(int B, int N, int M, int F, int C, int r, int K, int 
 size_t sph3d_rows_gemm_image_bytes(int K, int N);
 int sph3d_rows_gemm_pack(int K, int N, const float* weights, int trans, void* image, void* stream);
 int sph3d_rows_gemm(int R, int K, int N, int terms, const float* x, const void* image, float* y, void* stream);
+/* gw (K x N) = x^T * g, the weight gradient of the same product, summed over the R rows (csrc/rowswgrad.cu: both operands
+ * MN-major for the tensor core, so x (R x K) and g (R x N) are converted exactly as they lie in memory; one CTA per
+ * 128 x 128 block of gw and slab of rows, partial blocks in `workspace` summed in slab order -> deterministic).
+ * Same `terms` and alignment rules as sph3d_rows_gemm; workspace of sph3d_rows_wgrad_workspace_bytes(R, K, N) bytes. */
+size_t sph3d_rows_wgrad_workspace_bytes(int R, int K, int N);
+int sph3d_rows_wgrad(int R, int K, int N, int terms, const float* x, const float* g, float* gw,
+                     void* workspace, size_t workspace_bytes, void* stream);
 /* diagnostics: while `buffer` (6*64*4 int64 of device memory) is set, CTA (0,0) of every sph3d_rows_gemm launch records
  * clock64 stamps of its producer / issuer / epilogue steps there; NULL switches it off (the default). */
 void sph3d_rows_gemm_trace(void* buffer);

@@ -3,7 +3,7 @@
 (activation_fn default, :88-103) and tf.layers.batch_normalization(momentum=0.99, training=...) (:328-332).
 
 TEST INFRASTRUCTURE ONLY (tests/): the checker for csrc/post.cu (sph3d_bias_act_bn[_grad]) and csrc/dense_*.cu
-(sph3d_dense_gemm).  PARITY UNPINNED: TensorFlow 1.12 is not in this image and the reference ships no golden vectors for
+(sph3d_rows_gemm, sph3d_rows_wgrad).  PARITY UNPINNED: TensorFlow 1.12 is not in this image and the reference ships no golden vectors for
 these nodes, so this module restates their published definitions --
   elu(x)   = x                    for x > 0,  exp(x) - 1 otherwise           (tensorflow/core/kernels/relu_op_functor.h)
   elu'(x)  = 1 resp. exp(x)       (EluGrad: (activations + 1) * gradients)

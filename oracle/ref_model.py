@@ -99,5 +99,5 @@ def install(pkg, setattr_fn=None):
     put(u.tf_unpool3d, "weighted_interpolate", lambda i, w, a, b: WeightedUnpool.apply(i, w.detach(), a, b))
     put(u, "FUSED_TAIL", False)
     put(u, "SPLIT_K_WEIGHT_GRAD", False)
-    put(u, "TENSOR_CORE_DENSE", False)
+    put(u, "ROWS_GEMM", False)
     return undo

@@ -1,5 +1,6 @@
-"""Hand-written tcgen05 rows product (csrc/rowsgemm.cu) against a float64 product, the cuBLAS fp32 GEMM torch calls and
-the CUTLASS-collective instantiation it replaces (csrc/dense_gemm.cuh) on the layer shapes of the three networks.
+"""Hand-written tcgen05 products (csrc/rowsgemm.cu, csrc/rowswgrad.cu) against a float64 product and the cuBLAS fp32 GEMM torch calls
+on the layer shapes of the three networks (profiles/r2_rowsgemm.json also holds the timings of the CUTLASS-collective
+instantiation of round 1, measured with this script before that path was removed).
 
     python profiles/check_rowsgemm.py [--time]      (GPU box) -> one JSON line per shape and product
 """
@@ -61,15 +62,32 @@ def main():
                 img = rg.pack(w, trans)
                 lib = (lambda: g @ w.t()) if trans else (lambda: x @ w)
                 Kk, Nn = a.shape[1], out.shape[1]
-                old = (lambda: u._tc_gemm(1, g, w, R, Nn, Kk)) if trans else (lambda: u._tc_gemm(0, x, w, R, Nn, Kk))
                 rec["rows_gemm_ms"] = round(timeit(lambda: rg.rows_gemm(a, w, trans=trans, image=img)), 4)
                 rec["rows_gemm_2term_ms"] = round(timeit(lambda: rg.rows_gemm(a, w, trans=trans, image=img, terms=2)), 4)
                 rec["with_pack_ms"] = round(timeit(lambda: rg.rows_gemm(a, w, trans=trans)), 4)
                 rec["cublas_fp32_ms"] = round(timeit(lib), 4)
-                rec["cutlass_9xbf16_ms"] = round(timeit(old), 4) if old() is not None else None
                 bytes_ = 4.0 * R * (Kk + Nn)
                 rec["hbm_gbs"] = round(bytes_ / rec["rows_gemm_ms"] / 1e6, 1)
                 rec["tflops_fp32_equiv"] = round(2.0 * R * Kk * Nn / rec["rows_gemm_ms"] / 1e9, 1)
+            print(json.dumps(rec), flush=True)
+    if "--wgrad" in sys.argv:
+        for R, K, N, where in SHAPES:
+            x, g = torch.randn(R, K, device="cuda"), torch.randn(R, N, device="cuda")
+            ref = x.double().t() @ g.double()
+            mag = x.double().abs().t() @ g.double().abs()
+            rec = {"where": where, "product": "gw", "R": R, "K": K, "N": N}
+            for t in (3, 2):
+                out = rg.rows_wgrad(x, g, terms=t)
+                rec["rel_err_of_terms_%d" % t] = float(((out.double() - ref).abs() / mag.clamp_min(1e-30)).max())
+            rec["rel_err_fp32_gemm"] = float((((x.t() @ g).double() - ref).abs() / mag.clamp_min(1e-30)).max())
+            worst = max(worst, rec["rel_err_of_terms_3"])
+            if timing:
+                rec["rows_wgrad_ms"] = round(timeit(lambda: rg.rows_wgrad(x, g)), 4)
+                rec["rows_wgrad_2term_ms"] = round(timeit(lambda: rg.rows_wgrad(x, g, terms=2)), 4)
+                rec["cublas_fp32_ms"] = round(timeit(lambda: x.t() @ g), 4)
+                u.ROWS_GEMM = False
+                rec["split_k_library_ms"] = round(timeit(lambda: u._weight_grad(x, g)), 4)
+                u.ROWS_GEMM = True
             print(json.dumps(rec), flush=True)
     print(json.dumps({"worst_rel_err_of_terms": worst, "worst_rel_err_of_terms_2term": worst2, "ok": worst < 1e-5}))
     assert worst < 1e-5

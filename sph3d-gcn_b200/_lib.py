@@ -53,8 +53,6 @@ SIGNATURES = {
     "sph3d_bias_act_bn_workspace_bytes": (c_size_t, [c_int] * 2),
     "sph3d_bias_act_bn": (c_int, [c_int] * 4 + [c_float] * 2 + [_P] * 10 + [c_size_t, _P]),
     "sph3d_bias_act_bn_grad": (c_int, [c_int] * 4 + [_P] * 11 + [c_size_t, _P]),
-    "sph3d_dense_gemm_workspace_bytes": (c_size_t, [c_int] * 5),
-    "sph3d_dense_gemm": (c_int, [c_int] * 5 + [_P] * 4 + [c_size_t, _P]),
     "sph3d_separable_conv3d_supported": (c_int, [c_int] * 8),
     "sph3d_sepconv_weight_image_bytes": (c_size_t, [c_int] * 2),
     "sph3d_sepconv_pack_weights": (c_int, [c_int] * 2 + [_P] * 3),
@@ -63,6 +61,8 @@ SIGNATURES = {
     "sph3d_rows_gemm_pack": (c_int, [c_int] * 2 + [_P, c_int, _P, _P]),
     "sph3d_rows_gemm": (c_int, [c_int] * 4 + [_P] * 4),
     "sph3d_rows_gemm_trace": (None, [_P]),
+    "sph3d_rows_wgrad_workspace_bytes": (c_size_t, [c_int] * 3),
+    "sph3d_rows_wgrad": (c_int, [c_int] * 4 + [_P] * 4 + [c_size_t, _P]),
 }
 
 

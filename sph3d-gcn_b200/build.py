@@ -15,51 +15,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsph3d_b200.so")
 SOURCES = ["nnquery.cu", "buildkernel.cu", "conv_fwd.cu", "conv_bwd.cu", "conv_bwd_t.cu", "pool3d.cu", "sample.cu", "post.cu",
-           "sepconv.cu", "rowsgemm.cu",
-           "dense_nn.cu", "dense_nt.cu", "dense_tn.cu", "dense_nn2.cu", "dense_nt2.cu", "dense_abi.cu"]
-HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", "tc05.cuh", "dense_gemm.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
+           "sepconv.cu", "rowsgemm.cu", "rowswgrad.cu"]
+HEADERS = ["common.cuh", "rowwarp.cuh", "conv_common.cuh", "tc05.cuh", os.path.join("..", "..", "include", "sph3d_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
-
-
-def cutlass_root():
-    """CuTe/CUTLASS header tree vendored in the image (no /opt/cutlass): the dense_*.cu translation units instantiate
-    its sm_100 tcgen05 collectives.  Returns the directory that holds include/ and tools/util/include, or None."""
-    import importlib.util
-    cands = []
-    env = os.environ.get("SPH3D_CUTLASS_ROOT")
-    if env:
-        cands.append(env)
-    for pkg, rel in (("flashinfer", os.path.join("data", "cutlass")), ("tilelang", os.path.join("3rdparty", "cutlass"))):
-        try:
-            spec = importlib.util.find_spec(pkg)
-        except Exception:
-            spec = None
-        if spec and spec.submodule_search_locations:
-            cands.append(os.path.join(list(spec.submodule_search_locations)[0], rel))
-    for c in cands:
-        if os.path.exists(os.path.join(c, "include", "cutlass", "gemm", "collective", "builders", "sm100_9xBF16_umma_builder.inl")) \
-                and os.path.exists(os.path.join(c, "tools", "util", "include", "cutlass", "util", "packed_stride.hpp")):
-            return c
-    return None
-
-
-def _extra_flags(source):
-    if not source.startswith("dense_"):
-        return []
-    root = cutlass_root()
-    if root is None:
-        # No silent downgrade: without the header tree the tcgen05 pointwise products cannot be built and the layer
-        # library would quietly fall back to the library GEMM.  Point SPH3D_CUTLASS_ROOT at a CUTLASS >= 4.x checkout
-        # (the directory that holds include/ and tools/util/include), or opt out explicitly with SPH3D_NO_CUTLASS=1:
-        # the dense entry points then exist and return cudaErrorNotSupported (801).
-        if os.environ.get("SPH3D_NO_CUTLASS") == "1":
-            return ["-DSPH3D_NO_CUTLASS"]
-        raise RuntimeError("sph3d-gcn_b200: CuTe/CUTLASS headers not found (looked at $SPH3D_CUTLASS_ROOT and the trees "
-                           "vendored in the flashinfer / tilelang packages). Set SPH3D_CUTLASS_ROOT, or SPH3D_NO_CUTLASS=1 "
-                           "to build without the tcgen05 pointwise products.")
-    return ["-I", os.path.join(root, "include"), "-I", os.path.join(root, "tools", "util", "include"),
-            "--expt-relaxed-constexpr", "-w"]
 
 
 def _nvcc():
@@ -88,9 +47,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
     def deps_time(source):
-        # the CUTLASS instantiations (two minutes each) include nothing of this library but dense_gemm.cuh
-        hdrs = ["dense_gemm.cuh"] if source.startswith("dense_") and source != "dense_abi.cu" else HEADERS
-        return _newest([os.path.normpath(os.path.join(CSRC, h)) for h in hdrs] + [os.path.join(CSRC, source)])
+        return _newest([os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS] + [os.path.join(CSRC, source)])
     objs = []
     procs = []
     for s in SOURCES:
@@ -99,7 +56,7 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, s)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= deps_time(s):
             continue
-        cmd = [_nvcc()] + NVCC_FLAGS + _extra_flags(s) + ["-c", "-o", obj, src]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", obj, src]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

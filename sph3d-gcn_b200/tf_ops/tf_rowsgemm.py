@@ -46,3 +46,25 @@ def rows_gemm(x, weights, trans=False, image=None, terms=None):
         rc = _lib.lib().sph3d_rows_gemm(R, K, N, int(terms or TERMS), _lib.ptr(x), _lib.ptr(image), _lib.ptr(y), _lib.stream_ptr())
     _lib.check(rc, "rows_gemm")
     return y
+
+
+def rows_wgrad(x, g, terms=None):
+    """x (R, K), g (R, N) -> x.T @ g (K, N) fp32: the weight gradient of the rows product, summed over the rows in a fixed
+    order (csrc/rowswgrad.cu).  No autograd."""
+    x = _lib.cuda_tensor(x, torch.float32, 2, "x")
+    g = _lib.cuda_tensor(g, torch.float32, 2, "g")
+    R, K = x.shape
+    N = g.shape[1]
+    if g.shape[0] != R:
+        raise ValueError("x and g must have the same number of rows")
+    if not supported(R, K, N) or x.data_ptr() % 16 or g.data_ptr() % 16:
+        raise ValueError("rows_wgrad needs K and N multiples of 4 and 16-byte aligned rows")
+    L = _lib.lib()
+    ws_bytes = L.sph3d_rows_wgrad_workspace_bytes(R, K, N)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x.device)
+    gw = torch.empty((K, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.sph3d_rows_wgrad(R, K, N, int(terms or TERMS), _lib.ptr(x), _lib.ptr(g), _lib.ptr(gw), _lib.ptr(ws), ws_bytes,
+                                _lib.stream_ptr())
+    _lib.check(rc, "rows_wgrad")
+    return gw

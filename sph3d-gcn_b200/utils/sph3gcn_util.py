@@ -356,102 +356,63 @@ else:
 
 
     # ------------------------------------------------------------------ layers
-    # The pointwise product (tf.matmul over the B*M rows, sph3gcn_util.py:144-146) stays a library GEMM.  Its WEIGHT
-    # gradient x^T g is a (Cin x Cout) result reduced over R = B*M rows: 8-64 output tiles, which cuBLAS runs on as many
-    # SMs without splitting K (measured: 1.35 ms of a 12 ms S3DIS step in `simt_sgemm_64x64_nt` kernels).  Here the rows
-    # are cut into P slabs, one batched GEMM forms the P partial products on all SMs and they are summed in slab order
-    # (deterministic): explicit split-K.
-    SPLIT_K_WEIGHT_GRAD = True
+    # The pointwise product (tf.matmul over the B*M rows, sph3gcn_util.py:144-146) and its two gradients run on hand-written
+    # tcgen05 kernels at fp32 accuracy: y = x w and gx = g w^T through csrc/rowsgemm.cu (the weights re-packed per call into
+    # the tensor core's operand image, the rows cross HBM once as fp32 and are split into three bf16 terms in registers),
+    # gw = x^T g through csrc/rowswgrad.cu (both operands MN-major, one CTA per 128 x 128 block of gw and slab of rows,
+    # partial blocks summed in slab order: deterministic).  Measured on the layer shapes of the three networks
+    # (profiles/r2_rowsgemm.json): y / gx 1.3-1.9x the CUTLASS 9xBF16 collective instantiation of round 1 and 2-2.8x the
+    # fp32 library GEMM from 3 072 rows up; gw 1.5-1.9x the split-K CUTLASS form and 3-5x the library GEMM (which runs the
+    # 8-64 output tiles of x^T g on as many SMs without splitting the sum).  Anything the kernels do not take -- channel
+    # counts that are not multiples of 4 (the 3-channel input layer, the 13 / 50-class logits), a few hundred rows, CPU
+    # tensors -- stays on the library GEMM, the weight gradient then as an explicit split over row slabs.
+    ROWS_GEMM = True
+    ROWS_GEMM_MIN_ROWS = 1024
+    ROWS_GEMM_TERMS = 3            # 3: six cross products (error 1-2e-6 of the terms); 2: four (2-5e-6), ~1.25x faster
+    SPLIT_K_WEIGHT_GRAD = True     # library fallback of the weight gradient: batched GEMM over row slabs + ordered sum
     _SPLIT_K_MIN_ROWS = 4096
-    # The three products of a layer (y = x w, gx = g w^T, gw = x^T g) run on the tcgen05 tensor cores at fp32 accuracy
-    # (csrc/dense_gemm.cuh: operands split on chip into three BF16 terms, nine cross products accumulated in TMEM) when the
-    # shape allows TMA (channel counts multiples of 4) and the problem is large enough to fill the machine; anything else --
-    # the 3-channel input layer, the 13/40/50-class logits, CPU tensors -- stays on the library GEMM.
-    TENSOR_CORE_DENSE = True
-    DENSE_CTA_PAIR = True          # y / gx with cta_group::2 (a CTA pair per 256 x 128 tile): ops 3 / 4 of sph3d_dense_gemm, 5-8 % faster
 
 
-    def _tc_gemm(op, a, b, M, N, K, L=1):
-        """D[l] = A[l] B[l] in the layouts of include/sph3d_b200.h (sph3d_dense_gemm); None when the shape is not covered"""
-        from .. import _lib
-        if not (TENSOR_CORE_DENSE and a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32):
+    def _rows_ok(R, K, N, *tensors):
+        return (ROWS_GEMM and R >= ROWS_GEMM_MIN_ROWS and K % 4 == 0 and N % 4 == 0 and
+                all(t.is_cuda and t.dtype == torch.float32 and t.data_ptr() % 16 == 0 for t in tensors))
+
+
+    def _rows_gemm(x, w, trans):
+        """x @ w (trans False) or x @ w.T (trans True) through sph3d_rows_gemm; None when the shape is not covered"""
+        R, K = x.shape
+        N = w.shape[0] if trans else w.shape[1]
+        if not _rows_ok(R, K, N, x, w):
             return None
-        if M % 4 or N % 4 or K % 4 or (a.data_ptr() | b.data_ptr()) % 16:
-            return None
-        lib = _lib.lib()
-        if DENSE_CTA_PAIR and op in (0, 1):
-            op += 3
-        out = torch.empty((L, M, N) if L > 1 else (M, N), dtype=torch.float32, device=a.device)
-        ws_bytes = lib.sph3d_dense_gemm_workspace_bytes(op, M, N, K, L)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
-        with torch.cuda.device(a.device):
-            rc = lib.sph3d_dense_gemm(op, M, N, K, L, _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
-                                      _lib.stream_ptr())
-        if rc in (1, 801):                                 # shape not implementable / built without the tensor-core path
-            return None
-        _lib.check(rc, "dense_gemm")
-        return out
-
-
-    def _tc_pays(M, N):
-        """128 x 128 output tiles, one CTA each: measured (profiles/r1_dense.json) to beat the fp32 SIMT GEMM by 1.25-1.55x
-        when at least ~64 tiles exist and they are more than half full; a 64-wide output (half-empty tiles) or a short and
-        deep product (3072 x 256 over K = 2048: 48 tiles) is left to the library."""
-        tiles = ((M + 127) // 128) * ((N + 127) // 128)
-        return tiles >= 64 and M * N >= 0.55 * tiles * 16384
+        return tf_rowsgemm.rows_gemm(x, w, trans=trans, terms=ROWS_GEMM_TERMS)
 
 
     def _weight_grad(x, g):
         """x (R, Cin), g (R, Cout) -> x^T g (Cin, Cout)"""
         R, cin = x.shape
         cout = g.shape[1]
+        if _rows_ok(R, cin, cout, x, g):
+            return tf_rowsgemm.rows_wgrad(x, g, terms=ROWS_GEMM_TERMS)
         if not SPLIT_K_WEIGHT_GRAD or R < _SPLIT_K_MIN_ROWS:
             return x.t() @ g
-        tiles = ((cin + 127) // 128) * ((cout + 127) // 128) if TENSOR_CORE_DENSE and x.is_cuda else \
-            ((cin + 63) // 64) * ((cout + 63) // 64)
+        tiles = ((cin + 63) // 64) * ((cout + 63) // 64)
         sms = torch.cuda.get_device_properties(x.device).multi_processor_count if x.is_cuda else 148
         slabs = min(max((2 * sms + tiles - 1) // tiles, 1), R // 512)
         if slabs <= 1:
             return x.t() @ g
-        rows = (R // slabs) // 4 * 4                       # slab length a multiple of 4 rows (TMA strides)
+        rows = R // slabs
         main = rows * slabs
-        part = _tc_gemm(2, x, g, cin, cout, rows, slabs) if rows >= 4 and cin * cout >= 0.55 * tiles * 16384 else None
-        if part is None:
-            part = torch.bmm(x[:main].view(slabs, rows, cin).transpose(1, 2), g[:main].view(slabs, rows, cout))
-        out = part.sum(dim=0)
+        out = torch.bmm(x[:main].view(slabs, rows, cin).transpose(1, 2), g[:main].view(slabs, rows, cout)).sum(dim=0)
         if main < R:
             out = out + x[main:].t() @ g[main:]
         return out
-
-
-    # y = x w and gx = g w^T on the hand-written tcgen05 rows product (csrc/rowsgemm.cu; the weights are re-packed per call
-    # into the tensor core's operand image, the rows cross HBM once as fp32).  Measured on the layer shapes of the three
-    # networks (profiles/r2_rowsgemm.json): 1.3-1.9x the CUTLASS 9xBF16 instantiation it replaces and 2-2.8x the fp32
-    # library GEMM from 3 072 rows up; below ~1 000 rows the launch is the cost and the library GEMM stays.
-    ROWS_GEMM = True
-    ROWS_GEMM_MIN_ROWS = 1024
-    ROWS_GEMM_TERMS = 3            # 3: six cross products (error 1-2e-6 of the terms); 2: four (2-5e-6), ~1.25x faster
-
-
-    def _rows_gemm(x, w, trans):
-        """x @ w (trans False) or x @ w.T (trans True) through sph3d_rows_gemm; None when the shape is not covered"""
-        if not (ROWS_GEMM and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32):
-            return None
-        R, K = x.shape
-        N = w.shape[0] if trans else w.shape[1]
-        if R < ROWS_GEMM_MIN_ROWS or K % 4 or N % 4 or x.data_ptr() % 16:
-            return None
-        return tf_rowsgemm.rows_gemm(x, w, trans=trans, terms=ROWS_GEMM_TERMS)
 
 
     class _Dense(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, w):
             ctx.save_for_backward(x, w)
-            R, K = x.shape
             y = _rows_gemm(x, w, False)
-            if y is None and _tc_pays(R, w.shape[1]):
-                y = _tc_gemm(0, x, w, R, w.shape[1], K)
             return y if y is not None else x @ w
 
         @staticmethod
@@ -460,10 +421,7 @@ else:
             g = g.contiguous()
             gx = gw = None
             if ctx.needs_input_grad[0]:
-                R, N = g.shape
                 gx = _rows_gemm(g, w, True)
-                if gx is None and _tc_pays(R, w.shape[0]):
-                    gx = _tc_gemm(1, g, w, R, w.shape[0], N)
                 if gx is None:
                     gx = g @ w.t()
             if ctx.needs_input_grad[1]:
@@ -505,7 +463,7 @@ else:
             gw = _weight_grad(dw.reshape(-1, kp), g2) if ctx.needs_input_grad[2] else None
             gi = gf = None
             if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-                gdw = _tc_gemm(1, g2, kernel, g2.shape[0], kp, cout) if _tc_pays(g2.shape[0], kp) else None
+                gdw = _rows_gemm(g2, kernel, True)
                 if gdw is None:
                     gdw = g2 @ kernel.t()
                 gi, gf = tf_conv3d.backward_on_graph(inputs, depthwise_kernel, gdw.reshape(B, M, kp), ctx.graph)

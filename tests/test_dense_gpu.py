@@ -1,11 +1,13 @@
-"""Pointwise product on the tcgen05 tensor cores at fp32 accuracy (csrc/dense_gemm.cuh, C ABI sph3d_dense_gemm) against a
-float64 product.  Tolerance: 1e-5 of the result's scale (north_star), i.e. what the fp32 SIMT GEMM of the reference's
-tf.matmul delivers; a single-pass TF32 or BF16 product would miss it by two orders of magnitude."""
+"""The three products of a layer's pointwise product (y = x w, gx = g w^T, gw = x^T g) as the layer library routes them:
+hand-written tcgen05 kernels (csrc/rowsgemm.cu, csrc/rowswgrad.cu) at fp32 accuracy where the shape allows, the library
+GEMM elsewhere, against a float64 product.  Tolerance: 1e-5 of the result's scale (north_star), i.e. what the fp32 SIMT GEMM
+of the reference's tf.matmul delivers; a single-pass TF32 or BF16 product would miss it by two orders of magnitude.
+(The kernels themselves are tested against the elementwise bound in tests/test_rowsgemm_gpu.py.)"""
 import numpy as np
 import pytest
 import torch
 
-from common import assert_close
+from common import assert_close, assert_close_terms
 
 pytestmark = pytest.mark.gpu
 
@@ -14,25 +16,39 @@ def _ops(pkg):
     return pkg.sph3gcn_util
 
 
-@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("R,K,N", [(4096, 128, 128), (65536, 256, 128), (3072, 2048, 256), (20000, 72, 64), (2052, 36, 512)])
-def test_forward_and_input_gradient_products(pkg, monkeypatch, R, K, N, pair):
-    """pair = cta_group::2 kernels (a CTA pair per 256 x 128 tile, ops 3 / 4), else one CTA per 128 x 128 tile (ops 0 / 1)"""
+def test_forward_and_input_gradient_products(pkg, R, K, N):
     u = _ops(pkg)
-    monkeypatch.setattr(u, "DENSE_CTA_PAIR", pair)
     g = torch.Generator().manual_seed(R + K + N)
     x = (torch.randn(R, K, generator=g) * 2 + 0.5).cuda()
     w = (torch.randn(K, N, generator=g) * 0.3).cuda()
     go = torch.randn(R, N, generator=g).cuda()
-    y = u._tc_gemm(0, x, w, R, N, K)
-    assert y is not None, "tensor-core path refused an aligned shape"
+    y = u._rows_gemm(x, w, False)
+    assert y is not None, "the tensor-core path refused an aligned shape"
     assert_close(y.cpu().numpy(), (x.double() @ w.double()).cpu().numpy(), 1e-5, "y = x w (%d,%d,%d)" % (R, K, N))
-    gx = u._tc_gemm(1, go, w, R, K, N)
+    gx = u._rows_gemm(go, w, True)
     assert gx is not None
     assert_close(gx.cpu().numpy(), (go.double() @ w.double().t()).cpu().numpy(), 1e-5, "gx = g w^T (%d,%d,%d)" % (R, K, N))
 
 
-@pytest.mark.parametrize("R,K,N", [(65536, 256, 128), (6144, 512, 256), (50001, 72, 64)])
+@pytest.mark.parametrize("terms", [3, 2])
+@pytest.mark.parametrize("R,K,N", [(65536, 256, 128), (6144, 512, 256), (50001, 72, 64), (3072, 2048, 256), (1000, 68, 132),
+                                   (100, 4, 4), (40000, 128, 516)])
+def test_weight_gradient_kernel(pkg, R, K, N, terms):
+    """csrc/rowswgrad.cu against float64, elementwise bound; ragged rows (last stage, last slab), K / N tails, one and
+    many blocks of gw"""
+    rg = pkg.tf_rowsgemm
+    g = torch.Generator().manual_seed(R + 3 * K + N)
+    x = (torch.randn(R, K, generator=g) + 0.25).cuda()
+    go = torch.randn(R, N, generator=g).cuda()
+    gw = rg.rows_wgrad(x, go, terms=terms)
+    xd, gd = x.double(), go.double()
+    assert_close_terms(gw.cpu().numpy(), (xd.t() @ gd).cpu().numpy(), (xd.abs().t() @ gd.abs()).cpu().numpy(), 1e-5,
+                       "gw = x^T g (%d,%d,%d) terms=%d" % (R, K, N, terms))
+    assert torch.equal(gw, rg.rows_wgrad(x, go, terms=terms))       # slabs summed in a fixed order
+
+
+@pytest.mark.parametrize("R,K,N", [(65536, 256, 128), (6144, 512, 256), (50001, 72, 64), (50001, 3, 32), (8192, 64, 13)])
 def test_weight_gradient_split_k(pkg, R, K, N):
     u = _ops(pkg)
     g = torch.Generator().manual_seed(R)
@@ -48,14 +64,14 @@ def test_unaligned_shapes_fall_back_to_the_library_gemm(pkg):
     u = _ops(pkg)
     x = torch.randn(4096, 3, device="cuda")
     w = torch.randn(3, 32, device="cuda")
-    assert u._tc_gemm(0, x, w, 4096, 32, 3) is None                  # K = 3: no TMA
-    assert u._tc_gemm(0, torch.randn(4096, 64, device="cuda"), torch.randn(64, 13, device="cuda"), 4096, 13, 64) is None
+    assert u._rows_gemm(x, w, False) is None                          # K = 3: no 16-byte rows
+    assert u._rows_gemm(torch.randn(4096, 64, device="cuda"), torch.randn(64, 13, device="cuda"), False) is None
     y = u._dense(x, w)
     assert_close(y.cpu().numpy(), (x.double() @ w.double()).cpu().numpy(), 1e-5, "fallback product")
 
 
 def test_layer_with_and_without_tensor_cores(pkg):
-    """pointwise_conv3d end to end: same outputs and gradients with TENSOR_CORE_DENSE on and off"""
+    """pointwise_conv3d end to end: same outputs and gradients with the tensor-core products on and off"""
     u = _ops(pkg)
     torch.manual_seed(5)
     x = torch.randn(8, 2048, 64, device="cuda")
@@ -63,7 +79,7 @@ def test_layer_with_and_without_tensor_cores(pkg):
     res = []
     for on in (True, False):
         u.reset_variables()
-        u.TENSOR_CORE_DENSE = on
+        u.ROWS_GEMM = on
         try:
             torch.manual_seed(6)
             xg = x.clone().requires_grad_(True)
@@ -72,7 +88,7 @@ def test_layer_with_and_without_tensor_cores(pkg):
             v = u.named_variables()
             res.append([y.detach().cpu().numpy(), xg.grad.cpu().numpy(), v['tc/weights'].grad.cpu().numpy()])
         finally:
-            u.TENSOR_CORE_DENSE = True
+            u.ROWS_GEMM = True
     for i, (a, b) in enumerate(zip(*res)):
         assert_close(a, b, 2e-5, "tensor cores on vs off, item %d" % i)
 
