@@ -408,6 +408,21 @@ else:
         return out
 
 
+    # gx = g w^T and gw = x^T g of one layer depend on g only: the weight gradient is enqueued on a second stream and the
+    # current stream joins after it has enqueued the input gradient, so the two kernels run side by side.  Deep levels
+    # (1 000-6 000 rows) give each of them a few dozen CTAs and ~25 us of serial chunk chain; together they cost one chain.
+    # Stream-ordered, so a captured step (GraphedStep) gets a fork / join in its graph.
+    OVERLAP_WEIGHT_GRAD = True
+    _GRAD_STREAMS = {}
+
+
+    def _grad_stream(device):
+        key = (device.type, device.index)
+        if key not in _GRAD_STREAMS:
+            _GRAD_STREAMS[key] = torch.cuda.Stream(device=device)
+        return _GRAD_STREAMS[key]
+
+
     class _Dense(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, w):
@@ -420,11 +435,23 @@ else:
             x, w = ctx.saved_tensors
             g = g.contiguous()
             gx = gw = None
-            if ctx.needs_input_grad[0]:
+            want_gx, want_gw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            overlap = OVERLAP_WEIGHT_GRAD and want_gx and want_gw and g.is_cuda
+            if overlap:
+                cur, side = torch.cuda.current_stream(g.device), _grad_stream(g.device)
+                side.wait_stream(cur)                      # g (and x) are ready where the current stream stands
+                with torch.cuda.stream(side):
+                    gw = _weight_grad(x, g)
+                x.record_stream(side)
+                g.record_stream(side)
+            if want_gx:
                 gx = _rows_gemm(g, w, True)
                 if gx is None:
                     gx = g @ w.t()
-            if ctx.needs_input_grad[1]:
+            if overlap:
+                cur.wait_stream(side)
+                gw.record_stream(cur)
+            elif want_gw:
                 gw = _weight_grad(x, g)
             return gx, gw
 

@@ -108,3 +108,25 @@ def test_layer_products_against_numpy_oracle(pkg):
     assert_close(y.detach().cpu().numpy(), OL.dense(x, w), 1e-5, "y")
     assert_close(xd.grad.cpu().numpy(), gx, 1e-5, "grad_x")
     assert_close(wd.grad.cpu().numpy(), gw, 1e-5, "grad_w")
+
+
+def test_weight_gradient_on_the_second_stream_changes_nothing(pkg):
+    """OVERLAP_WEIGHT_GRAD: gw is enqueued on a side stream next to gx; results are bit-identical to the serial order"""
+    u = _ops(pkg)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(6144, 256, generator=g).cuda()
+    w = (torch.randn(256, 128, generator=g) * 0.2).cuda()
+    go = torch.randn(6144, 128, generator=g).cuda()
+    res = []
+    for on in (True, False):
+        u.OVERLAP_WEIGHT_GRAD = on
+        try:
+            for _ in range(3):                                      # repeated: a missing join would show up as a race
+                xd, wd = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+                y = u._dense(xd, wd)
+                (y * 2.0).backward(go)
+            torch.cuda.synchronize()
+            res.append((xd.grad.clone(), wd.grad.clone()))
+        finally:
+            u.OVERLAP_WEIGHT_GRAD = True
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
