@@ -225,6 +225,9 @@ int sph3d_separable_conv3d(int B, int N, int M, int F, int C, int r, int K, int 
  *   K and N multiples of 4, x / y / image 16-byte aligned, else cudaErrorInvalidValue (1). */
 size_t sph3d_rows_gemm_image_bytes(int K, int N);
 int sph3d_rows_gemm_pack(int K, int N, const float* weights, int trans, void* image, void* stream);
+/* weights (K x N): `image` for x * W (sph3d_rows_gemm_image_bytes(K, N) bytes) and `image_t` for g * W^T
+ * (sph3d_rows_gemm_image_bytes(N, K) bytes) in one launch -- what a training step needs of a layer */
+int sph3d_rows_gemm_pack_pair(int K, int N, const float* weights, void* image, void* image_t, void* stream);
 int sph3d_rows_gemm(int R, int K, int N, int terms, const float* x, const void* image, float* y, void* stream);
 /* gw (K x N) = x^T * g, the weight gradient of the same product, summed over the R rows (csrc/rowswgrad.cu: both operands
  * MN-major for the tensor core, so x (R x K) and g (R x N) are converted exactly as they lie in memory; one CTA per

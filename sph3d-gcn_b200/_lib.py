@@ -59,6 +59,7 @@ SIGNATURES = {
     "sph3d_separable_conv3d": (c_int, [c_int] * 8 + [_P] * 9 + [c_int] + [_P] * 3),
     "sph3d_rows_gemm_image_bytes": (c_size_t, [c_int] * 2),
     "sph3d_rows_gemm_pack": (c_int, [c_int] * 2 + [_P, c_int, _P, _P]),
+    "sph3d_rows_gemm_pack_pair": (c_int, [c_int] * 2 + [_P] * 4),
     "sph3d_rows_gemm": (c_int, [c_int] * 4 + [_P] * 4),
     "sph3d_rows_gemm_trace": (None, [_P]),
     "sph3d_rows_wgrad_workspace_bytes": (c_size_t, [c_int] * 3),

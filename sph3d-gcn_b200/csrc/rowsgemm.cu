@@ -86,27 +86,39 @@ struct RowsGemmSync {
 // x * W; trans = 1: W is (N x K) row-major and the product is x * W^T.  Row n of block mb is output column mb*128 + n.
 // One thread converts the eight k of one 16-byte chunk of a row and writes the chunk of each term with one 16-byte store;
 // n is the fastest thread index (trans = 0: coalesced reads; trans = 1: every thread reads one full 32-byte sector).
-__global__ void __launch_bounds__(256)
-rows_gemm_pack_kernel(int K, int N, int KC, int MB, int trans, const float* __restrict__ W, unsigned char* __restrict__ image)
+__device__ __forceinline__ void rows_gemm_pack_chunk(int t, int K, int N, int MB, int trans, const float* __restrict__ W,
+                                                     unsigned char* __restrict__ image)
 {
-    const int total = KC * MB * 128 * 8;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        const int n = t % 128, c = (t / 128) % 8, mb = (t / 1024) % MB, kc = t / (1024 * MB);
-        const int k0 = kc * UNIT_K + c * 8, co = mb * 128 + n;
-        uint32_t hi[4], mid[4], lo[4];
+    const int n = t % 128, c = (t / 128) % 8, mb = (t / 1024) % MB, kc = t / (1024 * MB);
+    const int k0 = kc * UNIT_K + c * 8, co = mb * 128 + n;
+    uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-            float v0 = 0.f, v1 = 0.f;
-            if (co < N) {
-                if (k0 + e < K) v0 = trans ? __ldg(W + (size_t)co * K + k0 + e) : __ldg(W + (size_t)(k0 + e) * N + co);
-                if (k0 + e + 1 < K) v1 = trans ? __ldg(W + (size_t)co * K + k0 + e + 1) : __ldg(W + (size_t)(k0 + e + 1) * N + co);
-            }
-            split3_pack2(v0, v1, hi[e / 2], mid[e / 2], lo[e / 2]);
+    for (int e = 0; e < 8; e += 2) {
+        float v0 = 0.f, v1 = 0.f;
+        if (co < N) {
+            if (k0 + e < K) v0 = trans ? __ldg(W + (size_t)co * K + k0 + e) : __ldg(W + (size_t)(k0 + e) * N + co);
+            if (k0 + e + 1 < K) v1 = trans ? __ldg(W + (size_t)co * K + k0 + e + 1) : __ldg(W + (size_t)(k0 + e + 1) * N + co);
         }
-        unsigned char* base = image + ((size_t)(kc * 3) * MB + mb) * RG_UNIT + unit_offset(n, c * 8);
-        *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(base + (size_t)MB * RG_UNIT) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-        *reinterpret_cast<uint4*>(base + (size_t)2 * MB * RG_UNIT) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        split3_pack2(v0, v1, hi[e / 2], mid[e / 2], lo[e / 2]);
+    }
+    unsigned char* base = image + ((size_t)(kc * 3) * MB + mb) * RG_UNIT + unit_offset(n, c * 8);
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + (size_t)MB * RG_UNIT) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+    *reinterpret_cast<uint4*>(base + (size_t)2 * MB * RG_UNIT) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// image of W for the product it is asked for (K, N, trans) and, when image2 != NULL, in the same launch the image of the
+// opposite orientation (N, K, !trans): a training step needs both x * W (forward) and g * W^T (input gradient)
+__global__ void __launch_bounds__(256)
+rows_gemm_pack_kernel(int K, int N, int trans, const float* __restrict__ W, unsigned char* __restrict__ image,
+                      unsigned char* __restrict__ image2)
+{
+    const int KC = (K + UNIT_K - 1) / UNIT_K, MB = (N + 127) / 128;
+    const int KC2 = (N + UNIT_K - 1) / UNIT_K, MB2 = (K + 127) / 128;
+    const int total = KC * MB * 1024, total2 = image2 ? KC2 * MB2 * 1024 : 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total + total2; t += gridDim.x * blockDim.x) {
+        if (t < total) rows_gemm_pack_chunk(t, K, N, MB, trans, W, image);
+        else rows_gemm_pack_chunk(t - total, N, K, MB2, !trans, W, image2);
     }
 }
 
@@ -343,19 +355,30 @@ extern "C" size_t sph3d_rows_gemm_image_bytes(int K, int N)
     return KC * 3 * MB * RG_UNIT;
 }
 
-extern "C" int sph3d_rows_gemm_pack(int K, int N, const float* weights, int trans, void* image, void* stream)
+static int rows_gemm_pack_launch(int K, int N, const float* weights, int trans, void* image, void* image2, void* stream)
 {
     g_last_launch_count = 0;
     if (K <= 0 || N <= 0 || !weights || !image) return (int)cudaErrorInvalidValue;
-    const int KC = (K + UNIT_K - 1) / UNIT_K, MB = (N + 127) / 128;
-    const long long total = (long long)KC * MB * 128 * 8;
+    const long long KC = (K + UNIT_K - 1) / UNIT_K, MB = (N + 127) / 128, KC2 = (N + UNIT_K - 1) / UNIT_K, MB2 = (K + 127) / 128;
+    const long long total = KC * MB * 1024 + (image2 ? KC2 * MB2 * 1024 : 0);
     if (total >= (1LL << 31)) return (int)cudaErrorInvalidValue;
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
-    rows_gemm_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(K, N, KC, MB, trans ? 1 : 0, weights,
-                                                                 static_cast<unsigned char*>(image));
+    rows_gemm_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(K, N, trans ? 1 : 0, weights, static_cast<unsigned char*>(image),
+                                                                 static_cast<unsigned char*>(image2));
     SPH3D_CHECK_LAUNCH();
     g_last_launch_count = 1;
     return 0;
+}
+
+extern "C" int sph3d_rows_gemm_pack(int K, int N, const float* weights, int trans, void* image, void* stream)
+{
+    return rows_gemm_pack_launch(K, N, weights, trans, image, nullptr, stream);
+}
+
+extern "C" int sph3d_rows_gemm_pack_pair(int K, int N, const float* weights, void* image, void* image_t, void* stream)
+{
+    if (!image_t) return (int)cudaErrorInvalidValue;
+    return rows_gemm_pack_launch(K, N, weights, 0, image, image_t, stream);
 }
 
 static long long* g_rows_gemm_dbg = nullptr;

@@ -24,6 +24,19 @@ def pack(weights, trans=False):
     return image
 
 
+def pack_pair(weights):
+    """weights (K, N) fp32 -> (image of x @ weights, image of g @ weights.T) in one launch"""
+    weights = _lib.cuda_tensor(weights, torch.float32, 2, "weights")
+    K, N = weights.shape
+    L = _lib.lib()
+    image = torch.empty((L.sph3d_rows_gemm_image_bytes(K, N),), dtype=torch.uint8, device=weights.device)
+    image_t = torch.empty((L.sph3d_rows_gemm_image_bytes(N, K),), dtype=torch.uint8, device=weights.device)
+    with torch.cuda.device(weights.device):
+        rc = L.sph3d_rows_gemm_pack_pair(K, N, _lib.ptr(weights), _lib.ptr(image), _lib.ptr(image_t), _lib.stream_ptr())
+    _lib.check(rc, "rows_gemm_pack_pair")
+    return image, image_t
+
+
 # bf16 terms per operand: 3 = six cross products (2^-24 of a product), 2 = four (2^-17); see include/sph3d_b200.h
 TERMS = 3
 

@@ -378,13 +378,13 @@ else:
                 all(t.is_cuda and t.dtype == torch.float32 and t.data_ptr() % 16 == 0 for t in tensors))
 
 
-    def _rows_gemm(x, w, trans):
+    def _rows_gemm(x, w, trans, image=None):
         """x @ w (trans False) or x @ w.T (trans True) through sph3d_rows_gemm; None when the shape is not covered"""
         R, K = x.shape
         N = w.shape[0] if trans else w.shape[1]
         if not _rows_ok(R, K, N, x, w):
             return None
-        return tf_rowsgemm.rows_gemm(x, w, trans=trans, terms=ROWS_GEMM_TERMS)
+        return tf_rowsgemm.rows_gemm(x, w, trans=trans, terms=ROWS_GEMM_TERMS, image=image)
 
 
     def _weight_grad(x, g):
@@ -427,6 +427,12 @@ else:
         @staticmethod
         def forward(ctx, x, w):
             ctx.save_for_backward(x, w)
+            ctx.image_t = None
+            R, K = x.shape
+            if ctx.needs_input_grad[0] and _rows_ok(R, K, w.shape[1], x, w):
+                # the weights' operand images of both orientations in one launch: g w^T in backward finds its own
+                image, ctx.image_t = tf_rowsgemm.pack_pair(w)
+                return _rows_gemm(x, w, False, image)
             y = _rows_gemm(x, w, False)
             return y if y is not None else x @ w
 
@@ -445,7 +451,7 @@ else:
                 x.record_stream(side)
                 g.record_stream(side)
             if want_gx:
-                gx = _rows_gemm(g, w, True)
+                gx = _rows_gemm(g, w, True, ctx.image_t)
                 if gx is None:
                     gx = g @ w.t()
             if overlap:

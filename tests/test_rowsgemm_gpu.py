@@ -56,6 +56,14 @@ def test_packed_image_is_reusable_and_rows_beyond_the_last_tile_are_untouched(pk
     assert torch.equal(buf[:R], a) and bool((buf[R:] == 7.0).all())
 
 
+def test_pair_pack_equals_two_packs(pkg):
+    rg = pkg.tf_rowsgemm
+    for K, N in ((68, 132), (256, 128), (4, 516)):
+        w = torch.randn(K, N, device="cuda")
+        a, b = rg.pack_pair(w)
+        assert torch.equal(a, rg.pack(w)) and torch.equal(b, rg.pack(w, trans=True))
+
+
 def test_refuses_what_it_cannot_do(pkg):
     rg = pkg.tf_rowsgemm
     x = torch.randn(64, 6, device="cuda")
