@@ -56,6 +56,7 @@ WORKLOADS = {
     "cfgT_r2": dict(B=32, N=10000, K=64, C=128, r=2, kernel=(8, 2, 2)),
     "s3dis_l1": dict(B=8, N=8192, K=64, C=64, r=2, kernel=(8, 2, 2)),
     "cfg1": dict(B=2, N=1024, K=20, C=3, r=2, kernel=(8, 2, 2)),
+    "cfg5": dict(B=4, N=65536, K=64, C=256, r=1, kernel=(8, 2, 2)),        # ScanNet stress shape (BASELINE configs[4])
 }
 MODEL_WORKLOADS = {"s3dis_model": "s3dis", "modelnet_model": "modelnet", "shapenet_model": "shapenet"}
 MODEL_SHAPE = {"modelnet": (32, 10000), "shapenet": (16, 2048), "s3dis": (8, 8192)}

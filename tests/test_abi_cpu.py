@@ -60,3 +60,10 @@ def test_workspace_queries_need_no_gpu(pkg):
     assert L.sph3d_farthest_point_sample_workspace_bytes(2, 200000, 10) == 2 * 200000 * 4
     assert L.sph3d_depthwise_conv3d_grad_workspace_bytes(32, 10000, 10000, 33, 128, 1, 64) > 0
     assert L.sph3d_depthwise_conv3d_grad_workspace_bytes(0, 1, 1, 1, 1, 1, 1) == 0
+    # layer products: three bf16 terms, units of 128 output columns x 64 k = 16 KB; one partial block of gw per row slab
+    assert L.sph3d_rows_gemm_image_bytes(256, 128) == 4 * 3 * 1 * 16384
+    assert L.sph3d_rows_gemm_image_bytes(68, 132) == 2 * 3 * 2 * 16384
+    assert L.sph3d_rows_gemm_image_bytes(0, 128) == 0
+    ws = L.sph3d_rows_wgrad_workspace_bytes(65536, 256, 128)
+    assert ws > 0 and ws % (256 * 128 * 4) == 0
+    assert L.sph3d_rows_wgrad_workspace_bytes(100, 4, 4) == 4 * 4 * 4            # a single slab
