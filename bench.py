@@ -22,6 +22,7 @@ saturating radius of BASELINE.md (this library's, bit-identical to the reference
             gather that actually bounds it.
   cpu_baseline  the CPU oracle port (oracle/sph3d_oracle.c, OpenMP) on a bounded sample, rank 0, N=1.
   ref_gpu   (extra) the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same inputs, same GPU.
+  layer_products (extra) the pointwise product this convolution feeds and its two gradients (hand-written tcgen05 kernels).
   model     (extra, unless --no-extras) one SPH3D_s3dis training step (BASELINE.json configs[3], global B=8, N=8192) as a
             CUDA graph, STRONG scaling over the ranks of this run (B/G clouds per rank), all gradients through bucketed
             all-reduces that overlap the backward pass.
@@ -213,6 +214,113 @@ def cpu_baseline(host, cfg, target_seconds=12.0):
     t = run(nb) if nb > 1 else t1
     return {"value": nb * cfg["N"] / t, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "%d of %d clouds of the same workload, conv fwd (fp32 reference order) + bwd (fp64), OpenMP, %.2f s" % (nb, B, t)}
+
+
+def layer_products(S, R, K, N, iters=10):
+    """(extra) the pointwise product of the layer this convolution feeds (tf.matmul of sph3gcn_util.py:144-146) and its two
+    gradients at the workload's shape: hand-written tcgen05 kernels (csrc/rowsgemm.cu, rowswgrad.cu) vs the fp32 library
+    GEMM, CUDA events, weights packed outside the timed calls."""
+    rg = S.tf_rowsgemm
+    x = torch.randn(R, K, device="cuda")
+    w = 0.1 * torch.randn(K, N, device="cuda")
+    g = torch.randn(R, N, device="cuda")
+    img, img_t = rg.pack_pair(w)
+
+    def t(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    rec = {"rows": R, "K": K, "N": N,
+           "y_ms": t(lambda: rg.rows_gemm(x, w, image=img)), "gx_ms": t(lambda: rg.rows_gemm(g, w, trans=True, image=img_t)),
+           "gw_ms": t(lambda: rg.rows_wgrad(x, g)),
+           "library_fp32_ms": {"y": t(lambda: x @ w), "gx": t(lambda: g @ w.t()), "gw": t(lambda: x.t() @ g)}}
+    rec["y_hbm_gbs"] = 4.0 * R * (K + N) / (rec["y_ms"] * 1e-3) / 1e9
+    return rec
+
+
+def sharded_conv_bench(S, args, cfg, world, rank, dev, dist, sampler, barrier, max_over_ranks):
+    """--workload <conv workload> --scaling strong: the FIXED global problem (cfg's B clouds) over all ranks.  With no more
+    ranks than clouds every rank takes whole clouds; with more (BASELINE configs[4]: B = 4 on 8 GPUs) the
+    world // B ranks of a cloud split its query points and the backward SUM-all-reduces grad_input inside that rank group
+    (utils/dist_util.query_sharded) -- the one real data-path exchange of this library; grad_filter joins the usual
+    weight-gradient all-reduce over all ranks.  The graph of a cloud is built whole on each of its ranks (graph-build
+    side, outside the timed step, as in the weak-scaling workload)."""
+    DU, C3 = S.utils.dist_util, S.tf_conv3d
+    B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
+    M = N
+    c0, c1, shard, nshards = DU.cloud_shard(rank, world, B)
+    host, radius, F = make_inputs(cfg, 1234 + 2, dev, S)              # every rank: the same global problem
+    d = {k: v[c0:c1].to(dev) if k != "W" else v.to(dev) for k, v in host.items() if k != "xyz"}
+    E = int(host["cnt"].sum().item())
+    group = None
+    if nshards > 1:                                                   # one group per cloud; every rank creates all of them
+        for c in range(B):
+            g = dist.new_group(ranks=list(range(c * nshards, (c + 1) * nshards)))
+            if c == c0:
+                group = g
+    m0, m1 = DU.shard_bounds(M, shard, nshards)
+    go = d["go"][:, m0:m1].contiguous()
+    x = d["x"].clone().requires_grad_(True)
+    Wp = d["W"].clone().requires_grad_(True)
+    buckets = DU.GradBuckets([Wp], n_buckets=1, average=False)
+    C3.SHARE_PLANS = False
+
+    def step():
+        x.grad = None
+        buckets.zero()
+        out, _ = DU.query_sharded(lambda i, a, b_, c: C3.depthwise_conv3d(i, Wp, a, b_, c), x,
+                                  [d["idx"], d["cnt"], d["filt"]], shard, nshards, group)
+        out.backward(go)
+        buckets.finish()
+        return out
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    barrier()
+    wall1 = time.perf_counter()
+    ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    clocks = sampler.result(wall0, wall1)
+    # check against the unsharded op on this rank's clouds (same operands, whole graph, no collective)
+    out = step().detach()
+    xf = d["x"].clone().requires_grad_(True)
+    Wf = d["W"].clone().requires_grad_(True)
+    full = C3.depthwise_conv3d(xf, Wf, d["idx"], d["cnt"], d["filt"])
+    full.backward(d["go"])
+    ok = bool(torch.allclose(out, full.detach()[:, m0:m1], rtol=1e-5, atol=1e-6) and
+              torch.allclose(x.grad, xf.grad, rtol=1e-4, atol=1e-5))
+    okt = torch.tensor([1.0 if ok else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        conf = conv_config(args.workload, cfg, F, radius, E, world, "strong")
+        conf["B_per_gpu"] = (c1 - c0) / nshards
+        conf["parallelism"] = "%d clouds over %d ranks: %s" % (B, world, "whole clouds per rank" if nshards == 1 else
+                                                               "%d ranks per cloud split its query points; grad_input "
+                                                               "all-reduced inside each cloud's rank group" % nshards)
+        line = {"metric": METRIC, "value": B * M / (ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": conf, "clocks": clocks, "gpu_launches": None,
+                "exchange": {"grad_input_allreduce_bytes_per_rank": (c1 - c0) * N * C * 4 if nshards > 1 else 0,
+                             "grad_filter_allreduce_bytes": F * C * r * 4 if world > 1 else 0,
+                             "query_shards_per_cloud": nshards},
+                "results_verified": bool(okt.item() > 0.5),
+                "e2e": None}
+        print(json.dumps(line))
 
 
 def ref_gpu_times(dev_in, cfg, F, iters=2):
@@ -588,6 +696,11 @@ def main():
         return
 
     # ------------------------------------------------------------------------------------------ conv workloads
+    if args.scaling == "strong":
+        sharded_conv_bench(S, args, WORKLOADS[args.workload], world, rank, dev, dist, sampler, barrier, max_over_ranks)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     C3 = S.tf_conv3d
     cfg = WORKLOADS[args.workload]
     B, N, K, C, r = cfg["B"], cfg["N"], cfg["K"], cfg["C"], cfg["r"]
@@ -765,6 +878,10 @@ def main():
                 line["ref_gpu"] = ref_gpu_times(d, cfg, F)
             except Exception as e:
                 line["ref_gpu"] = {"error": repr(e)}
+            try:
+                line["layer_products"] = layer_products(S, B * M, C * r, 128)
+            except Exception as e:
+                line["layer_products"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -10,6 +10,13 @@ GPUs and 'gloo' on CPU (tests/test_dist_gloo_cpu.py, world_size 2).
 
 Q1 caveat: the ball query's radius chain depends on the LOCAL batch index (i%32, i//32); for a
 per-rank batch <= 32 the i//32 term vanishes, so sharding does not change any result.
+
+Fewer clouds than ranks (BASELINE configs[4]: B = 4 on 8 GPUs; SURVEY.md section 8e "B < G"): the ranks that hold the
+SAME cloud split its QUERY points.  Graph construction stays whole per cloud (the radius chain depends on the query's
+index inside its cloud, so a sliced ball query would not be the reference's); the convolution is exact on any slice of
+the rows -- output rows [m0, m1) need only those rows of the graph -- and its backward needs ONE real exchange:
+grad_input is a sum over all rows that reference a point, i.e. over the shards, so it is all-reduced inside the cloud's
+rank group (`query_sharded`, NCCL over NVLink); grad_filter partial sums join the weight-gradient all-reduce as before.
 """
 import torch
 import torch.distributed as dist
@@ -26,6 +33,48 @@ def shard_batch(tensors, rank, world):
     """Slice every tensor of a list along dim 0 to this rank's clouds."""
     lo, hi = shard_bounds(tensors[0].shape[0], rank, world)
     return [t[lo:hi].contiguous() for t in tensors]
+
+
+def cloud_shard(rank, world, clouds):
+    """(first cloud, one past the last cloud, query shard, query shards) of `rank`: with world <= clouds every rank takes a
+    slice of whole clouds; with more ranks than clouds, world // clouds ranks share each cloud and split its query points."""
+    rank, world, clouds = int(rank), int(world), int(clouds)
+    if world <= clouds:
+        lo, hi = shard_bounds(clouds, rank, world)
+        return lo, hi, 0, 1
+    if world % clouds:
+        raise ValueError("more ranks than clouds: the number of ranks must be a multiple of the number of clouds")
+    per = world // clouds
+    return rank // per, rank // per + 1, rank % per, per
+
+
+class _SumGradOverGroup(torch.autograd.Function):
+    """identity in the forward pass; the gradient is SUM all-reduced over `group` (the ranks that hold other query shards
+    of the same clouds)"""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def query_sharded(op, input, index_tensors, shard, nshards, group=None):
+    """Rows [m0, m1) = shard_bounds(M, shard, nshards) of a row-wise graph op:  op(input, *sliced index tensors).
+
+    `op` is any op of the hot path whose output row m depends on row m of the index tensors only (depthwise_conv3d with
+    the filter bound, pooling, unpooling); `index_tensors` are (B, M, ...) tensors of the whole graph.  The returned rows
+    are exact; in the backward pass the gradient w.r.t. `input` is summed over `group`.  -> (output rows, (m0, m1))"""
+    m0, m1 = shard_bounds(index_tensors[0].shape[1], shard, nshards)
+    sliced = [t[:, m0:m1].contiguous() for t in index_tensors]
+    x = _SumGradOverGroup.apply(input, group) if nshards > 1 else input
+    return op(x, *sliced), (m0, m1)
 
 
 def flatten_grads(params):

@@ -20,6 +20,51 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _worker_query_shards(rank, world, port, out_dir):
+    """two ranks share every cloud and split its query points: outputs are exact slices, grad_input sums over the group"""
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from common import features, make_cloud
+    from importlib import import_module
+    du = import_module("sph3d_gcn_b200.utils.dist_util")
+
+    B, N, K, C, r = 1, 257, 16, 4, 2                       # one cloud, two ranks: cloud_shard -> shards 0 / 1 of 2
+    assert du.cloud_shard(rank, world, B) == (0, 1, rank, 2)
+    assert du.cloud_shard(1, 2, 4) == (2, 4, 0, 1) and du.cloud_shard(5, 8, 4) == (2, 3, 1, 2)
+    xyz = make_cloud(601, B, N)
+    idx, cnt, dst = O.build_sphere_neighbor(xyz, xyz, 0.25, None, K)
+    filt = O.spherical_kernel(xyz, xyz, idx, cnt, dst, 0.25, [8, 2, 2])
+    x, W, go = features(602, B, N, C), features(603, 33, C, r), features(604, B, N, C * r)
+
+    class OracleConv(torch.autograd.Function):           # the CPU oracle as the row-wise op
+        @staticmethod
+        def forward(ctx, inp, a, b, c):
+            ctx.save_for_backward(inp, a, b, c)
+            return torch.from_numpy(O.depthwise_conv3d(inp.numpy(), W, a.numpy(), b.numpy(), c.numpy(), 1).astype(np.float32))
+
+        @staticmethod
+        def backward(ctx, g):
+            inp, a, b, c = ctx.saved_tensors
+            gi, _ = O.depthwise_conv3d_grad(inp.numpy(), W, g.numpy(), a.numpy(), b.numpy(), c.numpy())
+            return torch.from_numpy(gi.astype(np.float32)), None, None, None
+
+    xt = torch.from_numpy(x).requires_grad_(True)
+    out, (m0, m1) = du.query_sharded(lambda i, a, b, c: OracleConv.apply(i, a, b, c), xt,
+                                     [torch.from_numpy(idx), torch.from_numpy(cnt), torch.from_numpy(filt)], rank, world)
+    out.backward(torch.from_numpy(go[:, m0:m1]))
+    full = O.depthwise_conv3d(x, W, idx, cnt, filt, 1)
+    gi_full, _ = O.depthwise_conv3d_grad(x, W, go, idx, cnt, filt)
+    ok_rows = np.allclose(out.detach().numpy(), full[:, m0:m1], rtol=1e-6, atol=1e-6)
+    ok_grad = np.allclose(xt.grad.numpy(), gi_full, rtol=1e-5, atol=1e-6)
+    np.save(os.path.join(out_dir, "qs_%d.npy" % rank), np.array([ok_rows, ok_grad, m0, m1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, out_dir):
     for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
         if p not in sys.path:
@@ -141,3 +186,12 @@ def test_grad_buckets_single_process():
     lin(torch.ones(2, 4)).sum().backward()
     assert lin.weight.grad.data_ptr() >= b.flat.data_ptr() and torch.allclose(lin.weight.grad, torch.full((3, 4), 2.0))
     b.close()
+
+
+def test_query_shards_of_one_cloud_gloo_world2(tmp_path):
+    """B < G: ranks that share a cloud split its query rows; the only exchange is the SUM of grad_input"""
+    port = _free_port()
+    mp.spawn(_worker_query_shards, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "qs_0.npy"), np.load(tmp_path / "qs_1.npy")
+    assert a[0] and a[1] and b[0] and b[1]
+    assert (a[2], a[3], b[2], b[3]) == (0, 129, 129, 257)
