@@ -249,7 +249,8 @@ extern "C" int sph3d_rows_wgrad(int R, int K, int N, int terms, const float* x, 
     if (workspace_bytes < geo.part_bytes || (long long)geo.KB * geo.NB > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
     RowsWgradArgs a{};
     a.R = (unsigned)R; a.rows_per_slab = geo.rows_per_slab; a.K = K; a.N = N; a.KB = geo.KB; a.NB = geo.NB;
-    a.x = x; a.g = g; a.part = static_cast<float*>(workspace);
+    a.x = x; a.g = g;
+    a.part = geo.slabs == 1 ? gw : static_cast<float*>(workspace);   // a single slab writes the result itself: no partial, no sum
     const size_t smem = sizeof(RowsWgradSync) + 1024 + (size_t)WG_STAGES * terms * 4 * WG_UNIT;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
@@ -264,8 +265,11 @@ extern "C" int sph3d_rows_wgrad(int R, int K, int N, int terms, const float* x, 
         rows_wgrad_kernel<2><<<grid, WG_WARPS * 32, smem, st>>>(a);
     }
     SPH3D_CHECK_LAUNCH();
-    const int rc = launch_reduce_partials((int)geo.slabs, (size_t)K * N, a.part, gw, st);
-    if (rc) return rc;
-    g_last_launch_count = 2;
+    g_last_launch_count = 1;
+    if (geo.slabs > 1) {
+        const int rc = launch_reduce_partials((int)geo.slabs, (size_t)K * N, a.part, gw, st);
+        if (rc) return rc;
+        g_last_launch_count = 2;
+    }
     return 0;
 }

@@ -368,13 +368,14 @@ else:
     # tensors -- stays on the library GEMM, the weight gradient then as an explicit split over row slabs.
     ROWS_GEMM = True
     ROWS_GEMM_MIN_ROWS = 1024
+    ROWS_WGRAD_MIN_ROWS = 128      # x^T g over a few hundred rows: 32x32-tile library kernels take ~50 us (one cloud per rank)
     ROWS_GEMM_TERMS = 3            # 3: six cross products (error 1-2e-6 of the terms); 2: four (2-5e-6), ~1.25x faster
     SPLIT_K_WEIGHT_GRAD = True     # library fallback of the weight gradient: batched GEMM over row slabs + ordered sum
     _SPLIT_K_MIN_ROWS = 4096
 
 
-    def _rows_ok(R, K, N, *tensors):
-        return (ROWS_GEMM and R >= ROWS_GEMM_MIN_ROWS and K % 4 == 0 and N % 4 == 0 and
+    def _rows_ok(R, K, N, *tensors, min_rows=None):
+        return (ROWS_GEMM and R >= (ROWS_GEMM_MIN_ROWS if min_rows is None else min_rows) and K % 4 == 0 and N % 4 == 0 and
                 all(t.is_cuda and t.dtype == torch.float32 and t.data_ptr() % 16 == 0 for t in tensors))
 
 
@@ -391,7 +392,7 @@ else:
         """x (R, Cin), g (R, Cout) -> x^T g (Cin, Cout)"""
         R, cin = x.shape
         cout = g.shape[1]
-        if _rows_ok(R, cin, cout, x, g):
+        if _rows_ok(R, cin, cout, x, g, min_rows=ROWS_WGRAD_MIN_ROWS):
             return tf_rowsgemm.rows_wgrad(x, g, terms=ROWS_GEMM_TERMS)
         if not SPLIT_K_WEIGHT_GRAD or R < _SPLIT_K_MIN_ROWS:
             return x.t() @ g
