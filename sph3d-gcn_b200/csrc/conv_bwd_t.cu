@@ -241,6 +241,45 @@ sort_segments_kernel(size_t nseg, const int* __restrict__ seg, unsigned* __restr
     }
 }
 
+// Sub-lists (one point, one bin class) longer than T_PART entries are cut into parts: part 0 stays with the point, parts
+// 1.. become OVERFLOW items {point, first entry, one past the last entry} of their class, which the gather kernel hands
+// out before the points.  The table lives in the plan's rank scratch, which is dead once the fill pass has run:
+// [G counters | G tables of `cap` items].  One thread per (point, class).
+constexpr int T_PART = 2048;
+
+__global__ void __launch_bounds__(256)
+build_overflow_kernel(size_t lists /* B*N*G */, int G, int SLOTS, int cap, const int* __restrict__ seg,
+                      int* __restrict__ hdr, int4* __restrict__ tab)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < lists; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t pt = t / (unsigned)G;
+        const int cls = (int)(t - pt * (unsigned)G);
+        const size_t s0 = pt * ((size_t)G * SLOTS) + (size_t)cls * SLOTS;
+        const int beg = __ldg(seg + s0), end = __ldg(seg + s0 + SLOTS);
+        const int extra = (end - beg - 1) / T_PART;                   // parts beyond the first
+        if (extra <= 0) continue;
+        const int base = atomicAdd(hdr + cls, extra);
+        for (int j = 0; j < extra && base + j < cap; j++) {           // cap = slots / T_PART + 1 can never be exceeded
+            const int b0 = beg + (j + 1) * T_PART;
+            tab[(size_t)cls * cap + base + j] = make_int4((int)pt, b0, min(end, b0 + T_PART), 0);
+        }
+    }
+}
+
+constexpr int T_SPLIT_MIN_ROWS = 16384;          // below this no sub-list of a ball-query graph gets long enough to matter
+struct TOver { bool split; int cap; size_t hdr_off, tab_off; };
+static inline TOver t_over(int B, int M, int K, const TGeom& g)
+{
+    TOver o{};
+    const size_t slots = (size_t)B * M * K;
+    o.cap = (int)(slots / T_PART + 1);
+    o.hdr_off = g.rank_off;
+    o.tab_off = g.rank_off + 256;
+    const size_t region = align256(slots * g.rank_bytes);
+    o.split = M > T_SPLIT_MIN_ROWS && g.FP > 1 && 256 + (size_t)g.G * o.cap * sizeof(int4) <= region && g.G <= 64;
+    return o;
+}
+
 // gs[row, :] = gO[row, :] / cnt[row]   (row = b*M + m < B*M);   gs[B*M, :] = 0      -- gs is (B*M + 1, Co)
 template <int V>
 __global__ void __launch_bounds__(256)
@@ -314,9 +353,10 @@ __device__ __forceinline__ void st_strip_smem(float* p, const float (&v)[VEC])
 // row of the padding edges) and the segment sums are plain adds.  FOLD = true: `gs` is grad_output itself, every entry
 // carries nn_count - 1 of its row in cb bits and the sums are FMAs with 1/cnt (padding edges: scale 0); no scaled copy
 // is written, at the price of one more staged word per edge (measured slower at Cfg-T: DESIGN.md 4.3).
-template <int VEC, int R, int THREADS, int DEPTH, bool FOLD>
+template <int VEC, int R, int THREADS, int DEPTH, bool FOLD, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow, int sb, int cb, int F, int C, int G, int SLOTS,
+                  int part, int over_cap, const int* __restrict__ over_hdr, const int4* __restrict__ over_tab,
                   const int* __restrict__ seg, const unsigned* __restrict__ entries, const float* __restrict__ gs,
                   const float* __restrict__ input, const float* __restrict__ filter,
                   float* __restrict__ grad_input, float* __restrict__ gw_partial)
@@ -363,28 +403,59 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow, int sb, int cb, int F,
     const unsigned W = gridDim.x * (NWARPS / G);         // warps of my class in the grid
     const unsigned segoff = (unsigned)(cls * SLOTS);
 
-    // stage "boundaries": lane 0 loads the start, lane 1 the end of my sub-list of point `row`
-    auto load_b = [&](unsigned row) {
+    // SPLIT (graphs of more than T_SPLIT_MIN_ROWS rows per cloud).  Work items of my class: first the OVERFLOW items --
+    // parts 1, 2, ... of the sub-lists longer than `part` entries (build_overflow_kernel; a hub referenced by tens of
+    // thousands of rows, as in the ScanNet-stress graph whose radius chain ends up keeping the same 64 lowest-index points
+    // for 90 % of its rows, is otherwise ONE warp's serial walk and the whole kernel's critical path) --, then every
+    // point's sub-list, capped at its first `part` entries.  Partial sums of a point meet in grad_input through the
+    // vector reductions the bin classes already use.  Without SPLIT an item is a point and the loop is the one measured
+    // at the headline shape (the three extra live values of the item form cost it 6 %: register spills).
+    const unsigned nov = (SPLIT && over_hdr) ? (unsigned)min(__ldg(over_hdr + cls), over_cap) : 0u;
+    const int4* otab = over_tab + (size_t)cls * over_cap;
+    const unsigned nitems = SPLIT ? nov + rows : rows;
+    // stage "boundaries": lane 0 loads the start, lane 1 the end of the item's entry range (SPLIT: lane 2 its point)
+    auto load_b = [&](unsigned it) {
         int bv = 0;
-        if (row < rows) {
-            const unsigned sb = row * FP + segoff;            // seg[s] = start of segment s; seg[nseg] = number of edges
-            if (lane == 0) bv = __ldg(seg + sb);
-            if (lane == 1) bv = __ldg(seg + sb + SLOTS);
+        if constexpr (SPLIT) {
+            if (it < nov) {
+                if (lane < 3) {
+                    const int4 o = __ldg(otab + it);
+                    bv = lane == 0 ? o.y : (lane == 1 ? o.z : o.x);
+                }
+            } else if (it < nitems) {
+                const unsigned pt = it - nov;
+                const unsigned sb = pt * FP + segoff;
+                if (lane == 0) bv = __ldg(seg + sb);
+                if (lane == 1) bv = __ldg(seg + sb + SLOTS);
+                if (lane == 2) bv = (int)pt;
+            }
+        } else {
+            if (it < rows) {
+                const unsigned sb = it * FP + segoff;         // seg[s] = start of segment s; seg[nseg] = number of edges
+                if (lane == 0) bv = __ldg(seg + sb);
+                if (lane == 1) bv = __ldg(seg + sb + SLOTS);
+            }
         }
         return bv;
     };
-    unsigned row = blockIdx.x * (NWARPS / G) + warp / G;
+    unsigned row = blockIdx.x * (NWARPS / G) + warp / G;  // item index (without SPLIT: the point)
     unsigned row1 = row + W;
-    // point i+1: boundaries resolved, entries + input strip in flight; point i+2: boundaries in flight
+    // item i+1: boundaries resolved, entries + input strip in flight; item i+2: boundaries in flight
     int bv2 = load_b(row);
-    int beg1, end1; unsigned e0_1 = 0, e1_1 = 0; float in1[VI];
-    auto stage_e = [&](unsigned r1, int bv) {
+    int beg1, end1; unsigned pt1 = 0, e0_1 = 0, e1_1 = 0; float in1[VI];
+    auto stage_e = [&](unsigned it, int bv) {
         beg1 = __shfl_sync(FULL_MASK, bv, 0); end1 = __shfl_sync(FULL_MASK, bv, 1);
+        unsigned pt = it;
+        if constexpr (SPLIT) {
+            pt = (unsigned)__shfl_sync(FULL_MASK, bv, 2);
+            pt1 = pt;
+            if (it >= nov) end1 = min(end1, beg1 + part);    // the rest of a long sub-list is among the overflow items
+        }
         e0_1 = 0; e1_1 = 0;
         if (end1 > beg1) {
             if (beg1 + lane < end1) e0_1 = __ldg(entries + beg1 + lane);
             if (beg1 + 32 + lane < end1) e1_1 = __ldg(entries + beg1 + 32 + lane);
-            VecIO<VI>::ld(in1, inl + (size_t)r1 * C, true);
+            VecIO<VI>::ld(in1, inl + (size_t)pt * C, true);
         }
     };
 #pragma unroll
@@ -392,17 +463,17 @@ conv_bwd_t_kernel(unsigned rows /* B*N */, unsigned zrow, int sb, int cb, int F,
     stage_e(row, bv2);
     bv2 = load_b(row1);
 
-    for (; row < rows;) {
-        const unsigned crow = row;
+    for (; row < nitems;) {
+        const unsigned crow = SPLIT ? pt1 : row;
         const int beg = beg1, end = end1;
         const unsigned ce0 = e0_1, ce1 = e1_1;
         float inx[VEC];                                   // in[b,n,c] expanded to my flat channels
 #pragma unroll
         for (int e = 0; e < VEC; e++) inx[e] = in1[e / R];
-        stage_e(row1, bv2);                               // loads for point i+1 (its boundaries arrived during point i-1)
+        stage_e(row1, bv2);                               // loads for item i+1 (its boundaries arrived during item i-1)
         row = row1;
         row1 += W;
-        bv2 = load_b(row1);                               // boundary loads for point i+2
+        bv2 = load_b(row1);                               // boundary loads for item i+2
         if (end <= beg) continue;
 
         float gi[VEC], T[VEC];
@@ -598,6 +669,19 @@ static int t_build_plan(int B, int N, int M, int F, int K, const TGeom& g, const
 #undef EDGES
     SPH3D_CHECK_LAUNCH();
     *launches += 4;
+    {   // overflow items of the gather kernel (in the rank scratch, which the fill pass has finished with)
+        const TOver o = t_over(B, M, K, g);
+        if (o.split) {
+            e = cudaMemsetAsync(plan + o.hdr_off, 0, 256, st);
+            if (e != cudaSuccess) return (int)e;
+            const size_t lists = (size_t)B * N * g.G;
+            build_overflow_kernel<<<grid_for(lists, 256, 8), 256, 0, st>>>(lists, g.G, g.SLOTS, o.cap, seg,
+                                                                            reinterpret_cast<int*>(plan + o.hdr_off),
+                                                                            reinterpret_cast<int4*>(plan + o.tab_off));
+            SPH3D_CHECK_LAUNCH();
+            *launches += 1;
+        }
+    }
     if (tunables().bwdt_sort == 1) {             // opt-in: canonical order inside every segment
         sort_segments_kernel<<<grid_for(g.nseg, 256, 16), 256, 0, st>>>(g.nseg, seg, ent);
         SPH3D_CHECK_LAUNCH();
@@ -647,19 +731,24 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     }
     dim3 grid(p.grid_x, p.chunks);
     const unsigned rows = (unsigned)((long long)B * N);
+    const TOver ov = t_over(B, M, K, g);
+    const int* ohdr = reinterpret_cast<const int*>(plan + ov.hdr_off);
+    const int4* otab = reinterpret_cast<const int4*>(plan + ov.tab_off);
+    const int opart = T_PART;
+#define LAUNCH_T3(V, RR, TH, DP, FO, SP)                                                                         \
+    do {                                                                                                         \
+        e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP, FO, SP>, p.smem);                                          \
+        if (e != cudaSuccess) return (int)e;                                                                     \
+        conv_bwd_t_kernel<V, RR, TH, DP, FO, SP><<<grid, TH, p.smem, st>>>(rows, zrow, g.sb, g.cb, F, C, g.G, g.SLOTS, opart, \
+                                                                           ov.cap, ohdr, otab, seg, ent, gsrc, input, filter, \
+                                                                           grad_input, part);                    \
+    } while (0)
 #define LAUNCH_T2(V, RR, TH, DP)                                                                                 \
     do {                                                                                                         \
-        if (g.fold) {                                                                                            \
-            e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP, true>, p.smem);                                        \
-            if (e != cudaSuccess) return (int)e;                                                                 \
-            conv_bwd_t_kernel<V, RR, TH, DP, true><<<grid, TH, p.smem, st>>>(rows, zrow, g.sb, g.cb, F, C, g.G, g.SLOTS, seg, ent, \
-                                                                             gsrc, input, filter, grad_input, part); \
-        } else {                                                                                                 \
-            e = set_smem(conv_bwd_t_kernel<V, RR, TH, DP, false>, p.smem);                                       \
-            if (e != cudaSuccess) return (int)e;                                                                 \
-            conv_bwd_t_kernel<V, RR, TH, DP, false><<<grid, TH, p.smem, st>>>(rows, zrow, g.sb, g.cb, F, C, g.G, g.SLOTS, seg, ent, \
-                                                                              gsrc, input, filter, grad_input, part); \
-        }                                                                                                        \
+        if (g.fold && ov.split) LAUNCH_T3(V, RR, TH, DP, true, true);                                            \
+        else if (g.fold) LAUNCH_T3(V, RR, TH, DP, true, false);                                                  \
+        else if (ov.split) LAUNCH_T3(V, RR, TH, DP, false, true);                                                \
+        else LAUNCH_T3(V, RR, TH, DP, false, false);                                                             \
     } while (0)
     const int depth = t_depth(p.threads / 32);
 #define LAUNCH_T(V, RR)                                                                                          \
@@ -678,6 +767,7 @@ static int t_run_main(int B, int N, int M, int F, int C, int r, int K, const TGe
     else if (p.vec == 1 && r == 1) LAUNCH_T(1, 1);
     else return (int)cudaErrorInvalidValue;
 #undef LAUNCH_T2
+#undef LAUNCH_T3
 #undef LAUNCH_T
     SPH3D_CHECK_LAUNCH();
     int rc = launch_reduce_partials((int)w.P, (size_t)F * Co, part, grad_filter, st);

@@ -565,3 +565,38 @@ def test_ops_are_cuda_graph_capturable(pkg, oracle):
         assert_close(A(out), oracle.depthwise_conv3d(x_np, A(W), oi, oc, of, 1), 1e-5)
         ti, tf = oracle.depthwise_conv3d_grad(x_np, A(W), A(go), oi, oc, of)
         assert_close(A(gi), ti, 1e-5); assert_close(A(gf), tf, 1e-5)
+
+
+@pytest.mark.parametrize("r", [1, 2])
+def test_transposed_backward_cuts_hub_lists_into_parts(r, pkg, tune):
+    """More than 16 384 rows per cloud: sub-lists longer than 2 048 entries are cut into overflow items (conv_bwd_t.cu,
+    build_overflow_kernel).  A synthetic hub graph -- 20 000 rows that all reference the same 4 points, so every
+    (point, bin class) list holds ~3 000 entries -- against a float64 evaluation of the gradient formulas, and one-call
+    against planned (the table lives in the plan)."""
+    B, N, M, K, C, F = 2, 4, 20000, 4, 32, 33
+    rng = np.random.default_rng(77)
+    idx = np.stack([np.stack([rng.permutation(N)[:K] for _ in range(M)]) for _ in range(B)]).astype(np.int32)
+    cnt = rng.integers(1, K + 1, size=(B, M)).astype(np.int32)
+    filt = rng.integers(0, F, size=(B, M, K)).astype(np.int32)
+    x = features(78, B, N, C)
+    W = (0.2 * features(79, F, C, r)).astype(np.float32)
+    go = features(80, B, M, C * r)
+    # gradient formulas in float64 (SURVEY Q13): out[b,m,c*r+j] = sum_k in[b,n_k,c] W[f_k,c,j] / cnt
+    gi = np.zeros((B, N, C)); gf = np.zeros((F, C, r))
+    g3 = go.reshape(B, M, C, r).astype(np.float64)
+    for b in range(B):
+        for k in range(K):
+            live = cnt[b] > k
+            m = np.nonzero(live)[0]
+            n, f = idx[b, m, k], filt[b, m, k]
+            gs = g3[b, m] / cnt[b, m, None, None]                       # (rows, C, r)
+            np.add.at(gi[b], n, (gs * W[f].astype(np.float64)).sum(-1))
+            np.add.at(gf, f, x[b, n].astype(np.float64)[:, :, None] * gs)
+    tune(SPH3D_BWD_ALGO="2")
+    gi1, gf1 = pkg.tf_conv3d.depthwise_conv3d_grad(T(x), T(W), T(go), T(idx), T(cnt), T(filt))
+    assert_close(A(gi1), gi, 1e-5, "grad_input with hub lists cut into parts")
+    assert_close(A(gf1), gf, 1e-5, "grad_filter with hub lists cut into parts")
+    plan = pkg.tf_conv3d.conv_transpose(T(idx), T(cnt), T(filt), F, N)
+    gi2, gf2 = pkg.tf_conv3d.depthwise_conv3d_grad_planned(T(x), T(W), T(go), T(cnt), plan, K)
+    assert_close(A(gi2), gi, 1e-5, "planned grad_input with hub lists cut into parts")
+    assert_close(A(gf2), gf, 1e-5, "planned grad_filter with hub lists cut into parts")
