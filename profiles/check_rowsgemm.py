@@ -111,7 +111,7 @@ def trace(R, K, N):
     _lib.lib().sph3d_rows_gemm_trace(None)
     t = buf.view(6, 64, 4).cpu()
     t0 = int(t[t > 0].min())
-    names = ["producer(warp0): begin / got stage / arrived / (data in regs)", "issuer: begin wait / rows ready / issued+committed",
+    names = ["producer(warp0): begin / got stage / arrived", "issuer: begin wait / rows ready / issued+committed",
              ] + ["epilogue(warp%d): begin wait / accumulator ready / stored / first 64 rows loaded" % q for q in range(4)]
     for r in range(6):
         print(names[r])

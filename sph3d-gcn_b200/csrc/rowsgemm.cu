@@ -47,9 +47,9 @@ constexpr int RG_AST_MAX = 3;                    // stages of the row operand (3
 constexpr int RG_WST_MAX = 8;                    // weight units in shared memory: a ring of 4, or the whole image (<= 8)
 constexpr int RG_WST_RING = 4;
 
-// mbarrier wait of this kernel's dedicated warps: plain try_wait polling (tc05::mbar_wait passes a 2 us suspend hint, which
-// suits warps that share issue slots with a gather loop but put a ~2 us sleep into every stage hand-over here: measured
-// 2.5 us per 64-k chunk whatever the shape).  Traps after ~2 s instead of hanging the device.
+// mbarrier wait of this kernel's dedicated warps: plain try_wait polling (no suspend-time hint; measured: with or without
+// the 2 us hint of tc05::mbar_wait the kernel runs the same, the roles here never share issue slots with a gather loop).
+// Traps after ~2 s instead of hanging the device.
 __device__ __forceinline__ void rg_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok = 0;
@@ -289,7 +289,6 @@ rows_gemm_kernel(const RowsGemmArgs a)
             if (g >= AST) rg_wait(a_empty + 8u * sa, ((g / AST) - 1u) & 1u);
             if (tr) a.dbg[(0 * 64 + g) * 4 + 1] = clock64();
             const uint32_t xbase = base + A_off + sa * NT * RG_UNIT;
-            if (tr) a.dbg[(0 * 64 + g) * 4 + 3] = (long long)__float_as_int(v[0].x) * 0 + clock64();   // after the data arrived
 #pragma unroll
             for (int p = 0; p < RG_PR; p++) {
                 const unsigned m = (unsigned)pw * (2u * RG_PR) + 2u * p + half;
