@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define SPH3D_B200_ABI_VERSION 4
+/* 5: sph3d_dense_gemm (CUTLASS instantiation) removed; sph3d_rows_gemm*, sph3d_rows_wgrad* added */
+#define SPH3D_B200_ABI_VERSION 5
 int sph3d_abi_version(void);
 
 /* Number of KERNELS (memsets excluded) the calling thread's most recent entry-point call enqueued (bench.py

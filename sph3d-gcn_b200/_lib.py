@@ -94,7 +94,7 @@ def lib():
         fn = getattr(handle, name)      # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if handle.sph3d_abi_version() != 4:
+    if handle.sph3d_abi_version() != 5:
         raise ImportError("sph3d-gcn_b200: ABI version mismatch in %s" % path)
     _LIB = handle
     return _LIB

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in _header_symbols():
         assert hasattr(lib, s), "missing export " + s
     assert set(pkg._lib.SIGNATURES) == set(_header_symbols())
-    assert pkg._lib.lib().sph3d_abi_version() == 4
+    assert pkg._lib.lib().sph3d_abi_version() == 5
 
 
 def test_no_cpu_fallback(pkg):
